@@ -1,0 +1,388 @@
+/*
+ * oracle/lz4.c — LZ4 block + LZ4 frame (LZ4F), CPU restatement.
+ * TEST INFRASTRUCTURE ONLY (see cj_oracle.h).
+ *
+ * Reference path being restated (arithmetic lives in lz4-sys 1.11.1+lz4-1.10.0, un-vendored,
+ * Cargo.lock:457-470):
+ *   block: src/lz4.rs:78-95    decompress_block        -> lz4::block::decompress_to_buffer -> LZ4_decompress_safe
+ *          src/lz4.rs:113-131  compress_block          -> lz4::block::compress_to_buffer   -> LZ4_compress_default/_fast
+ *          src/lz4.rs:140-216  *_block_into            (same callee; size-prefix handled by caller)
+ *          src/lz4.rs:226-229  compress_block_bound    -> LZ4_compressBound(+4)
+ *   frame: src/lz4.rs:27-65    compress/decompress(_into) -> lz4::{Encoder,Decoder} (LZ4F_*)
+ * Format: lz4_Block_format.md, lz4_Frame_format.md.  The decoder's acceptance rules follow
+ * LZ4_decompress_safe's documented end-of-block restrictions (MFLIMIT 12, LASTLITERALS 5) so
+ * that borderline-invalid streams are judged the same way; cross-checked by fuzzing against
+ * the system liblz4.so.1 in tests/test_oracle_lz4.py.
+ */
+#include "cj_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define ERR(code) (-(int64_t)(code))
+#define MINMATCH 4
+#define MFLIMIT 12
+#define LASTLITERALS 5
+#define LZ4_MAX_INPUT 0x7E000000u
+
+static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t ld64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline void st32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+
+size_t cjo_lz4_compress_bound(size_t n) { return n > LZ4_MAX_INPUT ? 0 : n + n / 255 + 16; }
+
+/* ---- block decode --------------------------------------------------------------------- */
+int64_t cjo_lz4_block_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    if (n == 0) return ERR(CJO_E_EMPTY);
+    if (cap == 0) return (n == 1 && src[0] == 0) ? 0 : ERR(CJO_E_DST_SMALL);
+    size_t ip = 0, op = 0;
+    for (;;) {
+        if (ip >= n) return ERR(CJO_E_TRUNCATED);
+        uint8_t token = src[ip++];
+        size_t len = token >> 4;
+        if (len == 15) { /* literal-length extension: must stop 15 bytes before the end */
+            if (n < 15 || ip >= n - 15) return ERR(CJO_E_TRUNCATED);
+            uint8_t b;
+            do {
+                b = src[ip++];
+                len += b;
+                if (ip > n - 15) return ERR(CJO_E_TRUNCATED);
+            } while (b == 255);
+        }
+        /* literals; a run that reaches the tail zone of input or output must be the last one */
+        if ((op + len + MFLIMIT > cap) || (ip + len + (2 + 1 + LASTLITERALS) > n)) {
+            if (ip + len != n) return (ip + len > n) ? ERR(CJO_E_TRUNCATED) : ERR(CJO_E_CORRUPT);
+            if (op + len > cap) return ERR(CJO_E_DST_SMALL);
+            memmove(dst + op, src + ip, len);
+            return (int64_t)(op + len);
+        }
+        memcpy(dst + op, src + ip, len);
+        ip += len;
+        op += len;
+        size_t off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8);
+        ip += 2;
+        len = token & 15;
+        if (len == 15) { /* match-length extension: must stop 4 bytes before the end */
+            uint8_t b;
+            do {
+                b = src[ip++];
+                len += b;
+                if (ip > n - (LASTLITERALS - 1)) return ERR(CJO_E_TRUNCATED);
+            } while (b == 255);
+        }
+        len += MINMATCH;
+        if (off == 0 || off > op) return ERR(CJO_E_OFFSET);
+        if (op + len + LASTLITERALS > cap) return ERR(CJO_E_DST_SMALL);
+        if (off >= len) {
+            memcpy(dst + op, dst + op - off, len);
+        } else {
+            for (size_t i = 0; i < len; i++) dst[op + i] = dst[op + i - off];
+        }
+        op += len;
+    }
+}
+
+/* ---- block encode: LZ4_compress_fast scheme (greedy, single hash probe, skip trigger 6) ---- */
+static inline uint32_t hash_u16(uint32_t seq) { return (seq * 2654435761u) >> (32 - 13); }
+static inline uint32_t hash_u32(uint64_t seq) { return (uint32_t)(((seq << 24) * 889523592379ull) >> (64 - 12)); }
+
+static size_t count_match(const uint8_t* a, const uint8_t* b, const uint8_t* blimit) {
+    const uint8_t* start = b;
+    while (b + 8 <= blimit) {
+        uint64_t x = ld64(a) ^ ld64(b);
+        if (x) return (size_t)(b - start) + (size_t)(__builtin_ctzll(x) >> 3);
+        a += 8; b += 8;
+    }
+    while (b < blimit && *a == *b) { a++; b++; }
+    return (size_t)(b - start);
+}
+
+int64_t cjo_lz4_block_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int accel) {
+    if (n > LZ4_MAX_INPUT) return ERR(CJO_E_TOO_BIG);
+    if (cap < cjo_lz4_compress_bound(n)) return ERR(CJO_E_DST_SMALL);
+    if (accel < 1) accel = 1;
+    if (accel > 65537) accel = 65537;
+    const int small = n < 65536 + MFLIMIT - 1; /* 16-bit table, 13-bit hash */
+    uint32_t* table = (uint32_t*)calloc(small ? 8192 : 4096, sizeof(uint32_t));
+    if (!table) return ERR(CJO_E_CORRUPT);
+#define HASH(p) (small ? hash_u16(ld32(p)) : hash_u32(ld64(p)))
+    const uint8_t* ip = src;
+    const uint8_t* anchor = src;
+    const uint8_t* iend = src + n;
+    const uint8_t* mflimit_p1 = iend - MFLIMIT + 1;
+    const uint8_t* matchlimit = iend - LASTLITERALS;
+    uint8_t* op = dst;
+    if (n < MFLIMIT + 1) goto last_literals;
+    table[HASH(ip)] = 0;
+    ip++;
+    uint32_t fwd_h = HASH(ip);
+    for (;;) {
+        const uint8_t* match;
+        uint8_t* token;
+        {
+            const uint8_t* fwd_ip = ip;
+            uint32_t step = 1, search = (uint32_t)accel << 6;
+            do {
+                uint32_t h = fwd_h;
+                ip = fwd_ip;
+                fwd_ip += step;
+                step = search++ >> 6;
+                if (fwd_ip > mflimit_p1) goto last_literals;
+                uint32_t cur = (uint32_t)(ip - src);
+                uint32_t mi = table[h];
+                fwd_h = HASH(fwd_ip);
+                table[h] = cur;
+                match = src + mi;
+                if (!small && mi + 65535 < cur) continue; /* too far */
+                if (ld32(match) == ld32(ip)) break;
+            } while (1);
+        }
+        while (ip > anchor && match > src && ip[-1] == match[-1]) { ip--; match--; }
+        {
+            size_t lit = (size_t)(ip - anchor);
+            token = op++;
+            if (lit >= 15) {
+                size_t l = lit - 15;
+                *token = 15 << 4;
+                for (; l >= 255; l -= 255) *op++ = 255;
+                *op++ = (uint8_t)l;
+            } else {
+                *token = (uint8_t)(lit << 4);
+            }
+            memcpy(op, anchor, lit);
+            op += lit;
+        }
+    next_match:
+        op[0] = (uint8_t)(ip - match);
+        op[1] = (uint8_t)((ip - match) >> 8);
+        op += 2;
+        {
+            size_t mc = count_match(match + MINMATCH, ip + MINMATCH, matchlimit);
+            ip += mc + MINMATCH;
+            if (mc >= 15) {
+                *token += 15;
+                mc -= 15;
+                for (; mc >= 255; mc -= 255) *op++ = 255;
+                *op++ = (uint8_t)mc;
+            } else {
+                *token += (uint8_t)mc;
+            }
+        }
+        anchor = ip;
+        if (ip >= mflimit_p1) break;
+        table[HASH(ip - 2)] = (uint32_t)(ip - 2 - src);
+        {
+            uint32_t h = HASH(ip);
+            uint32_t cur = (uint32_t)(ip - src);
+            uint32_t mi = table[h];
+            table[h] = cur;
+            match = src + mi;
+            if ((small || mi + 65535 >= cur) && ld32(match) == ld32(ip)) {
+                token = op++;
+                *token = 0;
+                goto next_match;
+            }
+        }
+        fwd_h = HASH(++ip);
+    }
+last_literals: {
+        size_t lit = (size_t)(iend - anchor);
+        if (lit >= 15) {
+            size_t l = lit - 15;
+            *op++ = 15 << 4;
+            for (; l >= 255; l -= 255) *op++ = 255;
+            *op++ = (uint8_t)l;
+        } else {
+            *op++ = (uint8_t)(lit << 4);
+        }
+        memcpy(op, anchor, lit);
+        op += lit;
+    }
+#undef HASH
+    free(table);
+    return (int64_t)(op - dst);
+}
+
+/* ---- LZ4 frame -------------------------------------------------------------------------- */
+#define LZ4F_MAGIC 0x184D2204u
+#define LZ4F_SKIP_LO 0x184D2A50u
+#define LZ4F_SKIP_HI 0x184D2A5Fu
+
+size_t cjo_lz4f_max_compressed_len(size_t n) {
+    size_t blocks = n / 65536 + 1;
+    return 19 + blocks * (4 + 65536 + 4) + 8;
+}
+
+int64_t cjo_lz4f_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int flags) {
+    /* This oracle encoder always emits INDEPENDENT 64 KiB blocks (bit0 is honoured as "set");
+     * linked-block frames are covered on the decode side with liblz4-produced inputs. */
+    const int csum = (flags >> 1) & 1, csize = (flags >> 2) & 1;
+    if (cap < cjo_lz4f_max_compressed_len(n)) return ERR(CJO_E_DST_SMALL);
+    uint8_t* op = dst;
+    st32(op, LZ4F_MAGIC);
+    op += 4;
+    uint8_t* desc = op;
+    *op++ = (uint8_t)(0x40 | 0x20 | (csize ? 0x08 : 0) | (csum ? 0x04 : 0));
+    *op++ = 0x40; /* 64 KiB max block */
+    if (csize) { uint64_t v = n; memcpy(op, &v, 8); op += 8; }
+    *op = (uint8_t)(cjo_xxh32(desc, (size_t)(op - desc), 0) >> 8);
+    op++;
+    size_t pos = 0;
+    uint8_t* tmp = (uint8_t*)malloc(cjo_lz4_compress_bound(65536));
+    if (!tmp) return ERR(CJO_E_CORRUPT);
+    while (pos < n) {
+        size_t blk = n - pos < 65536 ? n - pos : 65536;
+        int64_t c = cjo_lz4_block_compress(src + pos, blk, tmp, cjo_lz4_compress_bound(blk), 1);
+        if (c < 0) { free(tmp); return c; }
+        if ((size_t)c >= blk) { /* store uncompressed */
+            st32(op, (uint32_t)blk | 0x80000000u);
+            memcpy(op + 4, src + pos, blk);
+            op += 4 + blk;
+        } else {
+            st32(op, (uint32_t)c);
+            memcpy(op + 4, tmp, (size_t)c);
+            op += 4 + (size_t)c;
+        }
+        pos += blk;
+    }
+    free(tmp);
+    st32(op, 0);
+    op += 4;
+    if (csum) { st32(op, cjo_xxh32(src, n, 0)); op += 4; }
+    return (int64_t)(op - dst);
+}
+
+/* LZ4 block decode with a prefix window: the linked-block mode lets matches reach back into
+ * previously decoded output (dst_start .. dst+op). */
+static int64_t lz4_block_decode_linked(const uint8_t* src, size_t n, uint8_t* out_start, uint8_t* dst, size_t cap) {
+    /* generic spec-level decoder (LZ4F_decompress feeds LZ4_decompress_safe_usingDict) */
+    size_t ip = 0, op = 0;
+    size_t hist = (size_t)(dst - out_start);
+    if (n == 0) return ERR(CJO_E_EMPTY);
+    for (;;) {
+        if (ip >= n) return ERR(CJO_E_TRUNCATED);
+        uint8_t token = src[ip++];
+        size_t len = token >> 4;
+        if (len == 15) {
+            uint8_t b;
+            do {
+                if (ip >= n) return ERR(CJO_E_TRUNCATED);
+                b = src[ip++];
+                len += b;
+            } while (b == 255);
+        }
+        if (len > n - ip) return ERR(CJO_E_TRUNCATED);
+        if (len > cap - op) return ERR(CJO_E_DST_SMALL);
+        memcpy(dst + op, src + ip, len);
+        ip += len;
+        op += len;
+        if (ip == n) return (int64_t)op;
+        if (n - ip < 2) return ERR(CJO_E_TRUNCATED);
+        size_t off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8);
+        ip += 2;
+        len = token & 15;
+        if (len == 15) {
+            uint8_t b;
+            do {
+                if (ip >= n) return ERR(CJO_E_TRUNCATED);
+                b = src[ip++];
+                len += b;
+            } while (b == 255);
+        }
+        len += MINMATCH;
+        if (off == 0 || off > op + hist) return ERR(CJO_E_OFFSET);
+        if (len > cap - op) return ERR(CJO_E_DST_SMALL);
+        for (size_t i = 0; i < len; i++) dst[op + i] = dst[op + i - off];
+        op += len;
+    }
+}
+
+static int64_t lz4f_walk(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int want_len_only) {
+    size_t s = 0, d = 0;
+    while (s < n) {
+        if (n - s < 4) return ERR(CJO_E_TRUNCATED);
+        uint32_t magic = ld32(src + s);
+        if (magic >= LZ4F_SKIP_LO && magic <= LZ4F_SKIP_HI) {
+            if (n - s < 8) return ERR(CJO_E_TRUNCATED);
+            size_t sz = ld32(src + s + 4);
+            if (sz > n - s - 8) return ERR(CJO_E_TRUNCATED);
+            s += 8 + sz;
+            continue;
+        }
+        if (magic != LZ4F_MAGIC) return ERR(CJO_E_HEADER);
+        if (n - s < 7) return ERR(CJO_E_TRUNCATED);
+        const uint8_t* desc = src + s + 4;
+        uint8_t flg = desc[0], bd = desc[1];
+        if ((flg >> 6) != 1) return ERR(CJO_E_HEADER);
+        if (flg & 0x02) return ERR(CJO_E_HEADER); /* reserved bit */
+        if (bd & 0x8F) return ERR(CJO_E_HEADER);
+        int indep = (flg >> 5) & 1, bsum = (flg >> 4) & 1, csize = (flg >> 3) & 1, csum = (flg >> 2) & 1, dict = flg & 1;
+        int bid = (bd >> 4) & 7;
+        if (bid < 4) return ERR(CJO_E_HEADER);
+        size_t bmax = (size_t)1 << (8 + 2 * bid);
+        size_t dlen = 2 + (csize ? 8 : 0) + (dict ? 4 : 0);
+        if (n - s < 4 + dlen + 1) return ERR(CJO_E_TRUNCATED);
+        if (((cjo_xxh32(desc, dlen, 0) >> 8) & 0xff) != desc[dlen]) return ERR(CJO_E_CHECKSUM);
+        uint64_t content_size = 0;
+        if (csize) memcpy(&content_size, desc + 2, 8);
+        if (dict) return ERR(CJO_E_UNSUPPORTED);
+        s += 4 + dlen + 1;
+        size_t frame_start = d;
+        if (want_len_only && csize) {
+            /* still need to find the end of the frame to handle concatenation: walk blocks */
+        }
+        for (;;) {
+            if (n - s < 4) return ERR(CJO_E_TRUNCATED);
+            uint32_t bs = ld32(src + s);
+            s += 4;
+            if (bs == 0) break;
+            int stored = (bs >> 31) & 1;
+            size_t blen = bs & 0x7FFFFFFFu;
+            if (blen > bmax) return ERR(CJO_E_CORRUPT);
+            if (blen > n - s) return ERR(CJO_E_TRUNCATED);
+            if (bsum) {
+                if (n - s - blen < 4) return ERR(CJO_E_TRUNCATED);
+                if (cjo_xxh32(src + s, blen, 0) != ld32(src + s + blen)) return ERR(CJO_E_CHECKSUM);
+            }
+            if (want_len_only) {
+                if (stored) {
+                    d += blen;
+                } else {
+                    /* no size field per block: decode into scratch to learn the length */
+                    uint8_t* tmp = (uint8_t*)malloc(65536 + bmax);
+                    if (!tmp) return ERR(CJO_E_CORRUPT);
+                    /* lengths only need the token walk; reuse the decoder with a zeroed window */
+                    memset(tmp, 0, 65536);
+                    int64_t r = lz4_block_decode_linked(src + s, blen, tmp, tmp + 65536, bmax);
+                    free(tmp);
+                    if (r < 0) return r;
+                    d += (size_t)r;
+                }
+            } else if (stored) {
+                if (blen > cap - d) return ERR(CJO_E_DST_SMALL);
+                memcpy(dst + d, src + s, blen);
+                d += blen;
+            } else {
+                uint8_t* win = indep ? dst + d : dst + frame_start;
+                size_t room = cap - d < bmax ? cap - d : bmax;
+                int64_t r = lz4_block_decode_linked(src + s, blen, win, dst + d, room);
+                if (r < 0) return r;
+                d += (size_t)r;
+            }
+            s += blen + (bsum ? 4 : 0);
+        }
+        if (csum) {
+            if (n - s < 4) return ERR(CJO_E_TRUNCATED);
+            if (!want_len_only && cjo_xxh32(dst + frame_start, d - frame_start, 0) != ld32(src + s)) return ERR(CJO_E_CHECKSUM);
+            s += 4;
+        }
+        if (csize && content_size != (uint64_t)(d - frame_start)) return ERR(CJO_E_LEN_MISMATCH);
+    }
+    return (int64_t)d;
+}
+
+int64_t cjo_lz4f_decompressed_len(const uint8_t* src, size_t n) { return lz4f_walk(src, n, NULL, 0, 1); }
+
+int64_t cjo_lz4f_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    static uint8_t dummy;
+    return lz4f_walk(src, n, dst ? dst : &dummy, cap, 0);
+}
