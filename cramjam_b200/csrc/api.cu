@@ -1,0 +1,483 @@
+// api.cu — the extern "C" boundary of libcramjam_cuda.so (include/cramjam_cuda.h).
+//
+// Host-side plumbing only: context (device, stream, scratch arenas, pinned staging), batch
+// staging for CJ_HOST / CJ_PINNED callers, dispatch to the codec kernels.  No codec arithmetic
+// runs on the CPU here; if the CUDA device is missing every compute entry point fails loudly.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "synth.cuh"
+
+namespace cj {
+cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
+cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream);
+cudaError_t launch_synth(uint8_t* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, cudaStream_t stream);
+int frames_decompress(cj_ctx* ctx, int codec, int where, const cj_batch* batch);
+int frames_compress(cj_ctx* ctx, int codec, int where, const cj_batch* batch, const cj_params* params);
+}  // namespace cj
+
+static thread_local char g_err[512] = "";
+
+void cj_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            cj_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
+                         cudaGetErrorString(_e));                                                   \
+            return CJ_E_CUDA;                                                                       \
+        }                                                                                           \
+    } while (0)
+
+// Growable device / pinned scratch buffer.
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CJ_OK;
+        release();
+        size_t want = std::max(bytes + bytes / 8, (size_t)1 << 20);
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            cj_set_error("%s of %zu bytes failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc", want, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return CJ_E_NOMEM;
+        }
+        cap = want;
+        return CJ_OK;
+    }
+    void release() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct cj_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    unsigned* counters = nullptr;  // device work-queue counters
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    uint64_t launches = 0;
+    std::mutex mu;
+    Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;
+    cj_ctx() {
+        h_src.pinned = h_dst.pinned = h_desc.pinned = true;
+    }
+};
+
+extern "C" {
+
+int cj_abi_version(void) { return CJ_ABI_VERSION; }
+
+int cj_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* cj_last_error(void) { return g_err; }
+
+const char* cj_status_string(int32_t st) {
+    switch (st) {
+    case CJ_OK: return "ok";
+    case CJ_ST_EMPTY: return "corrupt input (empty)";
+    case CJ_ST_HEADER: return "corrupt input (invalid header)";
+    case CJ_ST_TRUNCATED: return "corrupt input (unexpected end of input)";
+    case CJ_ST_OFFSET: return "corrupt input (back-reference offset is zero or beyond the produced output)";
+    case CJ_ST_DST_SMALL: return "output buffer is too small";
+    case CJ_ST_LEN_MISMATCH: return "corrupt input (decompressed length does not match the header)";
+    case CJ_ST_CHECKSUM: return "corrupt input (checksum mismatch)";
+    case CJ_ST_CORRUPT: return "corrupt input";
+    case CJ_ST_UNSUPPORTED: return "unsupported feature in input";
+    case CJ_ST_TOO_BIG: return "input is too big";
+    default: return "unknown status";
+    }
+}
+
+int cj_ctx_create(int device, cj_ctx** out) {
+    if (!out) return CJ_E_INVALID_ARG;
+    *out = nullptr;
+    int n = cj_device_count();
+    if (n <= 0) {
+        cj_set_error("no CUDA device is available: libcramjam_cuda has no CPU fallback");
+        return CJ_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        cj_set_error("device %d out of range (have %d)", device, n);
+        return CJ_E_INVALID_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cj_ctx* c = new (std::nothrow) cj_ctx();
+    if (!c) return CJ_E_NOMEM;
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CUDA_TRY(cudaMalloc(&c->counters, 64 * sizeof(unsigned)));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    *out = c;
+    return CJ_OK;
+}
+
+void cj_ctx_destroy(cj_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_src.release(); c->d_dst.release(); c->d_desc.release();
+    c->h_src.release(); c->h_dst.release(); c->h_desc.release();
+    if (c->counters) cudaFree(c->counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int cj_ctx_set_stream(cj_ctx* c, void* s) {
+    if (!c) return CJ_E_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return CJ_OK;
+}
+
+int cj_ctx_synchronize(cj_ctx* c) {
+    if (!c) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CJ_OK;
+}
+
+uint64_t cj_ctx_launch_count(const cj_ctx* c) { return c ? c->launches : 0; }
+
+int cj_ctx_last_kernel_ms(cj_ctx* c, float* ms) {
+    if (!c || !ms) return CJ_E_INVALID_ARG;
+    if (!c->ev_valid) {
+        *ms = 0.f;
+        return CJ_OK;
+    }
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return CJ_OK;
+}
+
+size_t cj_compress_bound(cj_codec codec, size_t n) {
+    switch (codec) {
+    case CJ_SNAPPY_RAW: return 32 + n + n / 6;
+    case CJ_LZ4_BLOCK: return n > 0x7E000000u ? 0 : n + n / 255 + 16;
+    case CJ_SNAPPY_FRAMED: {
+        size_t chunks = (n + 65535) / 65536;
+        return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16;
+    }
+    case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8;
+    default: return 0;
+    }
+}
+
+}  // extern "C"
+
+// ---- kernel dispatch on a device-resident batch ------------------------------------------------
+static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params) {
+    if (b.n == 0) return CJ_OK;
+    cudaError_t e;
+    cudaEventRecord(c->ev0, c->stream);
+    if (!compress) {
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, c->counters, c->sm_count, c->stream);
+        else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
+    } else {
+        int accel = params && params->acceleration > 0 ? params->acceleration : 1;
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, c->counters, c->sm_count, accel, c->stream);
+        else { cj_set_error("codec %d has no device-resident batch encoder", codec); return CJ_E_INVALID_ARG; }
+    }
+    cudaEventRecord(c->ev1, c->stream);
+    c->ev_valid = true;
+    c->launches += 1;
+    if (e != cudaSuccess) {
+        cj_set_error("kernel launch failed: %s", cudaGetErrorString(e));
+        return CJ_E_CUDA;
+    }
+    return CJ_OK;
+}
+
+static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Parallel host memcpy over units (gather into / scatter out of the pinned staging buffers).
+template <class F>
+static void parallel_units(size_t n, size_t bytes, F&& f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = bytes < ((size_t)8 << 20) ? 1 : std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, n});
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=, &f]() {
+            for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; i++) f(i);
+        });
+    for (auto& t : th) t.join();
+}
+
+// Batch whose payload lives in host memory: stage -> H2D -> kernel -> D2H -> unstage.
+static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_batch* bt, const cj_params* params) {
+    const size_t n = bt->n;
+    if (n == 0) return CJ_OK;
+    if (n > 0xffffffffull) { cj_set_error("too many units"); return CJ_E_INVALID_ARG; }
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    uint8_t* hd = (uint8_t*)bt->dst_base;
+
+    // Are the units laid out as (near-)contiguous arenas already?  Then copy the whole span once
+    // and keep the caller's offsets (no per-unit packing).  Always true for engine-made arenas.
+    uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0, s_sum = 0, d_sum = 0;
+    for (size_t i = 0; i < n; i++) {
+        s_lo = std::min(s_lo, bt->src_off[i]); s_hi = std::max(s_hi, bt->src_off[i] + bt->src_len[i]); s_sum += bt->src_len[i];
+        d_lo = std::min(d_lo, bt->dst_off[i]); d_hi = std::max(d_hi, bt->dst_off[i] + bt->dst_cap[i]); d_sum += bt->dst_cap[i];
+    }
+    const bool direct = where == CJ_PINNED;
+    const bool s_span = direct && (s_hi - s_lo) <= s_sum + s_sum / 4 + 64 * n;
+    const bool d_span = direct && (d_hi - d_lo) <= d_sum + 16 * n;
+
+    // device-side layout
+    std::vector<uint64_t> so(n), doff(n);
+    size_t s_bytes, d_bytes;
+    if (s_span) {
+        for (size_t i = 0; i < n; i++) so[i] = bt->src_off[i] - s_lo;
+        s_bytes = (size_t)(s_hi - s_lo);
+    } else {
+        size_t acc = 0;
+        for (size_t i = 0; i < n; i++) { so[i] = acc; acc += align16((size_t)bt->src_len[i]); }
+        s_bytes = acc;
+    }
+    if (d_span) {
+        for (size_t i = 0; i < n; i++) doff[i] = bt->dst_off[i] - d_lo;
+        d_bytes = (size_t)(d_hi - d_lo);
+    } else {
+        size_t acc = 0;
+        for (size_t i = 0; i < n; i++) { doff[i] = acc; acc += align16((size_t)bt->dst_cap[i]); }
+        d_bytes = acc;
+    }
+    int rc;
+    if ((rc = c->d_src.ensure(s_bytes + 16))) return rc;
+    if ((rc = c->d_dst.ensure(d_bytes + 16))) return rc;
+    const size_t desc_bytes = n * (5 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+
+    // descriptors: [src_off | src_len | dst_off | dst_cap | dst_len(out) | status(out)]
+    uint64_t* hq = (uint64_t*)c->h_desc.p;
+    memcpy(hq, so.data(), n * 8);
+    memcpy(hq + n, bt->src_len, n * 8);
+    memcpy(hq + 2 * n, doff.data(), n * 8);
+    memcpy(hq + 3 * n, bt->dst_cap, n * 8);
+    uint64_t* dq = (uint64_t*)c->d_desc.p;
+    CUDA_TRY(cudaMemcpyAsync(dq, hq, n * 32, cudaMemcpyHostToDevice, c->stream));
+
+    // payload in
+    if (s_span) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_src.p, hs + s_lo, s_bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if ((rc = c->h_src.ensure(s_bytes + 16))) return rc;
+        uint8_t* stage = (uint8_t*)c->h_src.p;
+        parallel_units(n, s_bytes, [&](size_t i) { memcpy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
+        CUDA_TRY(cudaMemcpyAsync(c->d_src.p, stage, s_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+
+    cj::Batch b;
+    b.n = (uint32_t)n;
+    b.src_base = (const uint8_t*)c->d_src.p;
+    b.src_off = dq;
+    b.src_len = dq + n;
+    b.dst_base = (uint8_t*)c->d_dst.p;
+    b.dst_off = dq + 2 * n;
+    b.dst_cap = dq + 3 * n;
+    b.dst_len = dq + 4 * n;
+    b.status = (int32_t*)(dq + 5 * n);
+    if ((rc = run_device(c, codec, compress, b, params))) return rc;
+
+    // results
+    CUDA_TRY(cudaMemcpyAsync(hq + 4 * n, dq + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, c->stream));
+    bool tight = false;
+    if (d_span) {
+        // decompress into exact-size slots: the span is exactly the produced bytes when every unit
+        // filled its capacity; otherwise fall through to the per-unit path so that no byte past
+        // dst_len[i] of the caller's memory is touched.
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        tight = true;
+        const uint64_t* dl = hq + 4 * n;
+        for (size_t i = 0; i < n && tight; i++) tight = dl[i] == bt->dst_cap[i];
+        if (tight) CUDA_TRY(cudaMemcpyAsync(hd + d_lo, c->d_dst.p, d_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (!tight) {
+        if ((rc = c->h_dst.ensure(d_bytes + 16))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const uint64_t* dl = hq + 4 * n;
+        // copy back only the prefix of the arena that holds produced bytes
+        size_t last_end = 0;
+        for (size_t i = 0; i < n; i++) last_end = std::max(last_end, (size_t)(doff[i] + dl[i]));
+        uint8_t* stage = (uint8_t*)c->h_dst.p;
+        if (last_end) CUDA_TRY(cudaMemcpyAsync(stage, c->d_dst.p, last_end, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        parallel_units(n, last_end, [&](size_t i) { if (dl[i]) memcpy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); });
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(bt->dst_len, hq + 4 * n, n * 8);
+    memcpy(bt->status, hq + 5 * n, n * 4);
+    return CJ_OK;
+}
+
+static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_batch* bt, const cj_params* params) {
+    if (!c || !bt) { cj_set_error("null context or batch"); return CJ_E_INVALID_ARG; }
+    if (bt->n && (!bt->src_off || !bt->src_len || !bt->dst_off || !bt->dst_cap || !bt->dst_len || !bt->status)) {
+        cj_set_error("null descriptor array");
+        return CJ_E_INVALID_ARG;
+    }
+    std::lock_guard<std::mutex> g(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (codec == CJ_SNAPPY_FRAMED || codec == CJ_LZ4_FRAME || codec == CJ_ZSTD)
+        return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
+    if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
+    if (where == CJ_DEVICE) {
+        if (bt->n > 0xffffffffull) { cj_set_error("too many units"); return CJ_E_INVALID_ARG; }
+        cj::Batch b;
+        b.n = (uint32_t)bt->n;
+        b.src_base = (const uint8_t*)bt->src_base; b.src_off = bt->src_off; b.src_len = bt->src_len;
+        b.dst_base = (uint8_t*)bt->dst_base; b.dst_off = bt->dst_off; b.dst_cap = bt->dst_cap;
+        b.dst_len = bt->dst_len; b.status = bt->status;
+        return run_device(c, codec, compress, b, params);
+    }
+    return run_host(c, codec, compress, where, bt, params);
+}
+
+// Entry used by frames.cu for the block payloads it has already placed in device memory.
+int cj_run_device_batch(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params) {
+    return run_device(c, codec, compress, b, params);
+}
+cudaStream_t cj_ctx_stream(cj_ctx* c) { return c->stream; }
+int cj_ctx_sm_count(cj_ctx* c) { return c->sm_count; }
+int cj_run_host_batch(cj_ctx* c, int codec, bool compress, int where, const cj_batch* bt, const cj_params* params) {
+    return run_host(c, codec, compress, where, bt, params);
+}
+
+extern "C" {
+
+int cj_decompress_batch(cj_ctx* c, cj_codec codec, cj_mem where, const cj_batch* batch) {
+    return run_batch(c, (int)codec, false, (int)where, batch, nullptr);
+}
+
+int cj_compress_batch(cj_ctx* c, cj_codec codec, cj_mem where, const cj_batch* batch, const cj_params* params) {
+    return run_batch(c, (int)codec, true, (int)where, batch, params);
+}
+
+static int single(cj_ctx* c, cj_codec codec, bool compress, const void* src, size_t n, void* dst, size_t cap, size_t* written,
+                  const cj_params* params) {
+    uint64_t so = 0, sl = n, dof = 0, dc = cap, dl = 0;
+    int32_t st = 0;
+    static uint8_t dummy[16];
+    cj_batch b;
+    b.n = 1;
+    b.src_base = src ? src : dummy; b.src_off = &so; b.src_len = &sl;
+    b.dst_base = dst ? dst : dummy; b.dst_off = &dof; b.dst_cap = &dc;
+    b.dst_len = &dl; b.status = &st;
+    int rc = run_batch(c, (int)codec, compress, CJ_HOST, &b, params);
+    if (rc) return rc;
+    if (written) *written = (size_t)dl;
+    if (st != CJ_OK) {
+        cj_set_error("%s", cj_status_string(st));
+        return CJ_E_UNIT_FAILED;
+    }
+    return CJ_OK;
+}
+
+int cj_decompress(cj_ctx* c, cj_codec codec, const void* src, size_t n, void* dst, size_t cap, size_t* written) {
+    return single(c, codec, false, src, n, dst, cap, written, nullptr);
+}
+
+int cj_compress(cj_ctx* c, cj_codec codec, const void* src, size_t n, void* dst, size_t cap, size_t* written, const cj_params* params) {
+    return single(c, codec, true, src, n, dst, cap, written, params);
+}
+
+int cj_synth_blocks(cj_ctx* c, cj_mem where, void* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index) {
+    if (!dst && n_blocks != 0 && block_len != 0) return CJ_E_INVALID_ARG;
+    if (where == CJ_DEVICE) {
+        if (!c) return CJ_E_INVALID_ARG;
+        std::lock_guard<std::mutex> g(c->mu);
+        CUDA_TRY(cudaSetDevice(c->device));
+        cudaError_t e = cj::launch_synth((uint8_t*)dst, n_blocks, block_len, seed, first_index, c->stream);
+        c->launches += 1;
+        if (e != cudaSuccess) { cj_set_error("synth launch failed: %s", cudaGetErrorString(e)); return CJ_E_CUDA; }
+        return CJ_OK;
+    }
+    // host generator: same function, used for CPU baselines and parity fixtures (no ctx needed)
+    uint8_t* out = (uint8_t*)dst;
+    parallel_units(n_blocks, n_blocks * block_len, [&](size_t i) { cj::synth_block(out + i * block_len, block_len, seed, first_index + i); });
+    return CJ_OK;
+}
+
+int cj_device_alloc(cj_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); cj_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return CJ_E_NOMEM; }
+    return CJ_OK;
+}
+int cj_device_free(cj_ctx* c, void* p) {
+    if (!c) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaFree(p));
+    return CJ_OK;
+}
+int cj_pinned_alloc(cj_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); cj_set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return CJ_E_NOMEM; }
+    return CJ_OK;
+}
+int cj_pinned_free(cj_ctx* c, void* p) {
+    if (!c) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaFreeHost(p));
+    return CJ_OK;
+}
+int cj_memcpy_h2d(cj_ctx* c, void* d, const void* s, size_t bytes) {
+    if (!c) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, c->stream));
+    return CJ_OK;
+}
+int cj_memcpy_d2h(cj_ctx* c, void* d, const void* s, size_t bytes) {
+    if (!c) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return CJ_OK;
+}
+
+}  // extern "C"
