@@ -42,7 +42,9 @@ for name in codecs:
     t_so, t_sl, t_do, t_dc = i64(po), i64(lens), i64(so), i64(np.full(n, U, np.uint64))
     t_dl = torch.zeros(n, dtype=torch.int64, device=dev); t_st = torch.zeros(n, dtype=torch.int32, device=dev)
     c = capi.Context(0)
-    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c.set_stream(stream.cuda_stream)
     for it in range(3):
         c.decompress_batch(codec, capi.DEVICE, n, t_src, t_so, t_sl, t_dst, t_do, t_dc, t_dl, t_st)
     torch.cuda.synchronize()
