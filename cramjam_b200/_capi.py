@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libcramjam_cuda.so")
+SO_PATH = os.environ.get("CJ_LIB_PATH") or os.path.join(HERE, "libcramjam_cuda.so")  # override: kernel A/B builds only
 
 SNAPPY_RAW, SNAPPY_FRAMED, LZ4_BLOCK, LZ4_FRAME, ZSTD = range(5)
 HOST, PINNED, DEVICE = range(3)

@@ -29,12 +29,27 @@
 
 namespace cj {
 
-constexpr int ORING = 8192;   // output ring bytes per warp
-constexpr int IRING = 4096;   // input ring bytes per warp
-constexpr int QCAP = 64;      // element queue entries per warp
+#ifndef CJ_ORING
+#define CJ_ORING 4096
+#endif
+#ifndef CJ_IRING
+#define CJ_IRING 2048
+#endif
+#ifndef CJ_TMAX
+#define CJ_TMAX 1024
+#endif
+#ifndef CJ_DEC_CTAS
+#define CJ_DEC_CTAS 8
+#endif
+constexpr int ORING = CJ_ORING;   // output ring bytes per warp
+constexpr int IRING = CJ_IRING;   // input ring bytes per warp
+constexpr int QCAP = 64;          // element queue entries per warp
 constexpr uint32_t OMASK = ORING - 1, IMASK = IRING - 1;
-constexpr uint32_t TMAX = 2048;             // max output bytes of one lane-parallel batch
-constexpr uint32_t PARSE_SPAN = 2048;       // max compressed bytes between first queued element and parse cursor
+constexpr uint32_t TMAX = CJ_TMAX;            // max output bytes of one lane-parallel batch
+constexpr uint32_t PARSE_SPAN = IRING / 2 - 512;  // max compressed bytes between first queued element and parse cursor
+// refill() leaves at least IRING-1022 bytes resident past the first queued element; a parse window
+// starting inside the span looks at most 31 + 288 bytes further (largest lane-parallel element).
+static_assert(IRING >= PARSE_SPAN + 1022 + 352, "input ring too small");
 constexpr uint32_t FAR_T = ORING - TMAX;    // back-reference distance beyond which the source is re-read from global
 constexpr int STEP_CONT = -1, STEP_DONE = 0;  // serial step results (else a CJ_ST_* error)
 
@@ -62,10 +77,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 struct OutRing {
-    static constexpr uint32_t CHUNK = 1024;    // largest span moved between room checks (serial path)
-    static constexpr uint32_t FLUSH_T = 2048;  // drain when this many bytes are pending
+    static constexpr uint32_t CHUNK = ORING / 8;    // largest span moved between room checks (serial path)
+    static constexpr uint32_t FLUSH_T = ORING / 4;  // drain when this many bytes are pending
     static_assert(ORING >= 2 * CHUNK + FLUSH_T + 16, "ring too small for the far-match invariant");
-    static_assert(ORING >= TMAX + FLUSH_T + 16, "ring too small for a batch");
+    static_assert(ORING >= TMAX + FLUSH_T + CHUNK + 64, "ring too small for a batch");
+    static_assert(ORING >= 2 * TMAX + FLUSH_T + CHUNK + 32, "far sources of a batch must already be drained");
 
     uint32_t ring;     // shared-space address of this warp's output ring
     uint8_t* dst;
@@ -381,6 +397,22 @@ __device__ __forceinline__ void lane_copy16(uint32_t sp, uint32_t dp, uint32_t n
     }
 }
 
+// Same, source in global memory (drained output re-read through L1/L2; plain coherent loads).
+__device__ __forceinline__ void lane_copy16_global(const uint8_t* gp, uint32_t dp, uint32_t nl) {
+    const uint32_t mx = __reduce_max_sync(FULL, nl);
+    for (uint32_t b = 0; b < mx; b += 4) {
+        uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (b < nl) v0 = gp[b];
+        if (b + 1 < nl) v1 = gp[b + 1];
+        if (b + 2 < nl) v2 = gp[b + 2];
+        if (b + 3 < nl) v3 = gp[b + 3];
+        if (b < nl) sts8(dp + b, v0);
+        if (b + 1 < nl) sts8(dp + b + 1, v1);
+        if (b + 2 < nl) sts8(dp + b + 2, v2);
+        if (b + 3 < nl) sts8(dp + b + 3, v3);
+    }
+}
+
 // Executes the first cnt (<= 32) queued elements, one lane each.  Returns how many were executed
 // (a prefix); 0 means the first element must go through the serial path.
 template <int CODEC>
@@ -437,11 +469,30 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
     if ((uint32_t)lane >= k) { LL = 0; ML = 0; }
     const uint32_t T = __shfl_sync(FULL, incl, k - 1);
 
-    // ---- literals: always ready ----
+    // Per-lane addressing.  m = where the match part lands; se = end of the distinct source bytes it needs.
+    const uint32_t m = o + LL;
+    const uint32_t se = m - off + min(ML, off);
+    const uint32_t ldi = (o + out.a) & OMASK, lsi = (lsrc + in.a) & IMASK;
+    const uint32_t mdi = (m + out.a) & OMASK, msi = (m - off + out.a) & OMASK;
+    const bool shortL = LL != 0 && LL <= 16 && ldi + LL <= (uint32_t)ORING && lsi + LL <= (uint32_t)IRING;
+    const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING;  // lane-parallel candidates
+    const bool nearM = smallM && off <= FAR_T && msi + ML <= (uint32_t)ORING;              // source in the ring
+    const bool farM = smallM && off > FAR_T;                                               // source re-read from global (L1/L2)
+    bool pending = ML != 0;
+
+    // ---- pass 1: literals (always ready); for snappy also every copy whose source precedes the batch ----
     {
-        const uint32_t di = (o + out.a) & OMASK, si = (lsrc + in.a) & IMASK;
-        const bool shortL = LL != 0 && LL <= 16 && di + LL <= (uint32_t)ORING && si + LL <= (uint32_t)IRING;
-        lane_copy16(in.ring + si, out.ring + di, shortL ? LL : 0u);
+        uint32_t sp = in.ring + lsi, dp = out.ring + ldi, nl = shortL ? LL : 0u;
+        bool early = false;
+        if (CODEC == CJ_SNAPPY_RAW) {
+            early = pending && se <= O;
+            if (early && nearM) { sp = out.ring + msi; dp = out.ring + mdi; nl = ML; }
+        }
+        lane_copy16(sp, dp, nl);
+        if (CODEC == CJ_SNAPPY_RAW) {
+            lane_copy16_global(out.dst + (m - off), out.ring + mdi, (early && farM) ? ML : 0u);
+            if (early && (nearM || farM)) pending = false;
+        }
         uint32_t lm = __ballot_sync(FULL, LL != 0 && !shortL);
         while (lm) {
             const int j = __ffs(lm) - 1;
@@ -454,26 +505,23 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
 
     // ---- back-references: dependency rounds ----
     {
-        const uint32_t m = o + LL;                    // where this lane's match lands
-        const uint32_t se = m - off + min(ML, off);   // end of the distinct source bytes it needs
-        const uint32_t di = (m + out.a) & OMASK, si = (m - off + out.a) & OMASK;
-        const bool shortM = ML != 0 && ML <= 16 && off >= ML && off <= FAR_T && di + ML <= (uint32_t)ORING && si + ML <= (uint32_t)ORING;
-        bool pending = ML != 0;
         uint32_t pm = __ballot_sync(FULL, pending);
         while (pm) {
             const uint32_t F = __shfl_sync(FULL, m, __ffs(pm) - 1);  // all output below F is complete
             const bool ready = pending && se <= F;
-            lane_copy16(out.ring + si, out.ring + di, (ready && shortM) ? ML : 0u);
-            uint32_t lm = __ballot_sync(FULL, ready && !shortM);
-            while (lm) {
+            lane_copy16(out.ring + msi, out.ring + mdi, (ready && nearM) ? ML : 0u);
+            lane_copy16_global(out.dst + (m - off), out.ring + mdi, (ready && farM) ? ML : 0u);
+            uint32_t lm = __ballot_sync(FULL, ready && !nearM && !farM);
+            while (lm) {  // long, self-overlapping or ring-wrapping copies: the whole warp moves one at a time
                 const int j = __ffs(lm) - 1;
                 lm &= lm - 1;
                 const uint32_t jm = __shfl_sync(FULL, m, j), jl = __shfl_sync(FULL, ML, j), jf = __shfl_sync(FULL, off, j);
                 const uint32_t s = jm - jf;
-                for (uint32_t i = lane; i < jl; i += 32) {
-                    const uint32_t idx = jf < jl ? i % jf : i;
-                    const uint32_t v = jf > FAR_T ? (uint32_t)__ldcg(out.dst + s + idx) : lds8(out.ridx(s + idx));
-                    sts8(out.ridx(jm + i), v);
+                if (jf >= jl) {
+                    if (jf > FAR_T) for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), out.dst[s + i]);
+                    else for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i)));
+                } else {
+                    for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i % jf)));
                 }
             }
             pending = pending && !ready;
@@ -569,7 +617,7 @@ constexpr int DEC_WARPS = 4;
 constexpr int DEC_SMEM_WARP = ORING + IRING + QCAP * 4;
 
 template <int CODEC, bool FAST>
-__global__ void __launch_bounds__(DEC_WARPS * 32) lz_decode_kernel(Batch b, unsigned* __restrict__ counter) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz_decode_kernel(Batch b, unsigned* __restrict__ counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -606,7 +654,7 @@ static cudaError_t launch_one(const Batch& b, unsigned* counter, int sm_count, c
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    int grid = sm_count * 4;  // 4 CTAs x 4 warps x 12.25 KiB of shared memory per SM
+    int grid = sm_count * CJ_DEC_CTAS;  // CTAs per SM x 4 warps x (ORING + IRING + 256 B) of shared memory
     const int need = (int)((b.n + DEC_WARPS - 1) / DEC_WARPS);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
