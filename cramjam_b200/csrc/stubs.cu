@@ -2,7 +2,6 @@
 #include "common.cuh"
 void cj_set_error(const char* fmt, ...);
 namespace cj {
-cudaError_t launch_lz_encode(int, const Batch&, unsigned*, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 int frames_decompress(cj_ctx*, int codec, int, const cj_batch*) { cj_set_error("codec %d decode not built yet", codec); return CJ_E_INVALID_ARG; }
 int frames_compress(cj_ctx*, int codec, int, const cj_batch*, const cj_params*) { cj_set_error("codec %d encode not built yet", codec); return CJ_E_INVALID_ARG; }
 }
