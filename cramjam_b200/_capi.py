@@ -65,6 +65,7 @@ def lib():
         "cj_decompress": ([vp, C.c_int, vp, sz, vp, sz, C.POINTER(sz)], C.c_int),
         "cj_compress": ([vp, C.c_int, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Params)], C.c_int),
         "cj_synth_blocks": ([vp, C.c_int, vp, sz, sz, u64, u64], C.c_int),
+        "cj_copy_units": ([vp, sz, vp, vp, vp, vp, vp], C.c_int),
         "cj_device_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),
         "cj_device_free": ([vp, vp], C.c_int),
         "cj_pinned_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),
@@ -160,6 +161,9 @@ class Context:
         b = self._batch(n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, dst_len, status)
         p = Params(level, acceleration, 0)
         _check(lib().cj_compress_batch(self._h, codec, where, C.byref(b), C.byref(p)))
+
+    def copy_units(self, n, src_base, src_off, lens, dst_base, dst_off):
+        _check(lib().cj_copy_units(self._h, n, _ptr(src_base), _ptr(src_off), _ptr(lens), _ptr(dst_base), _ptr(dst_off)))
 
     def synth_device(self, dst, n_blocks, block_len, seed=0xC0FFEE, first_index=0):
         _check(lib().cj_synth_blocks(self._h, DEVICE, _ptr(dst), n_blocks, block_len, seed, first_index))

@@ -20,6 +20,8 @@
 namespace cj {
 cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
 cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream);
+cudaError_t launch_copy_units(uint32_t n, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* len, uint8_t* dst_base,
+                              const uint64_t* dst_off, int sm_count, cudaStream_t stream);
 cudaError_t launch_synth(uint8_t* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, cudaStream_t stream);
 int frames_decompress(cj_ctx* ctx, int codec, int where, const cj_batch* batch);
 int frames_compress(cj_ctx* ctx, int codec, int where, const cj_batch* batch, const cj_params* params);
@@ -439,6 +441,17 @@ int cj_synth_blocks(cj_ctx* c, cj_mem where, void* dst, size_t n_blocks, size_t 
     // host generator: same function, used for CPU baselines and parity fixtures (no ctx needed)
     uint8_t* out = (uint8_t*)dst;
     parallel_units(n_blocks, n_blocks * block_len, [&](size_t i) { cj::synth_block(out + i * block_len, block_len, seed, first_index + i); });
+    return CJ_OK;
+}
+
+int cj_copy_units(cj_ctx* c, size_t n, const void* src_base, const uint64_t* src_off, const uint64_t* len, void* dst_base,
+                  const uint64_t* dst_off) {
+    if (!c || n > 0xffffffffull) return CJ_E_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cj::launch_copy_units((uint32_t)n, (const uint8_t*)src_base, src_off, len, (uint8_t*)dst_base, dst_off, c->sm_count, c->stream);
+    c->launches += 1;
+    if (e != cudaSuccess) { cj_set_error("copy_units launch failed: %s", cudaGetErrorString(e)); return CJ_E_CUDA; }
     return CJ_OK;
 }
 

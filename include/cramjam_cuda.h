@@ -135,6 +135,12 @@ int cj_compress(cj_ctx* ctx, cj_codec codec, const void* src, size_t src_len, vo
 int cj_synth_blocks(cj_ctx* ctx, cj_mem where, void* dst, size_t n_blocks, size_t block_len, uint64_t seed,
                     uint64_t first_index);
 
+/* ---- batched unit copy on the device (all pointers device memory; asynchronous on the stream):
+ *      dst_base[dst_off[i] .. +len[i]) = src_base[src_off[i] .. +len[i]).  Packs the ragged output of
+ *      cj_compress_batch into a dense arena, splices block payloads into frame containers. ------- */
+int cj_copy_units(cj_ctx* ctx, size_t n, const void* src_base, const uint64_t* src_off, const uint64_t* len, void* dst_base,
+                  const uint64_t* dst_off);
+
 /* ---- device memory helpers for hosts that have no CUDA runtime binding of their own -------- */
 int cj_device_alloc(cj_ctx* ctx, size_t bytes, void** out);
 int cj_device_free(cj_ctx* ctx, void* p);
