@@ -60,6 +60,7 @@ def lib():
         "cj_ctx_last_kernel_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "cj_compress_bound": ([C.c_int, sz], sz),
         "cj_decompressed_len": ([C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
+        "cj_decompress_bound": ([C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
         "cj_decompress_batch": ([vp, C.c_int, C.c_int, C.POINTER(Batch)], C.c_int),
         "cj_compress_batch": ([vp, C.c_int, C.c_int, C.POINTER(Batch), C.POINTER(Params)], C.c_int),
         "cj_decompress": ([vp, C.c_int, vp, sz, vp, sz, C.POINTER(sz)], C.c_int),

@@ -3,29 +3,8 @@
 // Host-side plumbing only: context (device, stream, scratch arenas, pinned staging), batch
 // staging for CJ_HOST / CJ_PINNED callers, dispatch to the codec kernels.  No codec arithmetic
 // runs on the CPU here; if the CUDA device is missing every compute entry point fails loudly.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <thread>
-#include <vector>
-
-#include "common.cuh"
+#include "internal.h"
 #include "synth.cuh"
-
-namespace cj {
-cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
-cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream);
-cudaError_t launch_copy_units(uint32_t n, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* len, uint8_t* dst_base,
-                              const uint64_t* dst_off, int sm_count, cudaStream_t stream);
-cudaError_t launch_synth(uint8_t* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, cudaStream_t stream);
-int frames_decompress(cj_ctx* ctx, int codec, int where, const cj_batch* batch);
-int frames_compress(cj_ctx* ctx, int codec, int where, const cj_batch* batch, const cj_params* params);
-}  // namespace cj
 
 static thread_local char g_err[512] = "";
 
@@ -35,62 +14,6 @@ void cj_set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
 }
-
-#define CUDA_TRY(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess) {                                                                    \
-            cj_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
-                         cudaGetErrorString(_e));                                                   \
-            return CJ_E_CUDA;                                                                       \
-        }                                                                                           \
-    } while (0)
-
-// Growable device / pinned scratch buffer.
-struct Scratch {
-    void* p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return CJ_OK;
-        release();
-        size_t want = std::max(bytes + bytes / 8, (size_t)1 << 20);
-        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            cap = 0;
-            cj_set_error("%s of %zu bytes failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc", want, cudaGetErrorString(e));
-            (void)cudaGetLastError();
-            return CJ_E_NOMEM;
-        }
-        cap = want;
-        return CJ_OK;
-    }
-    void release() {
-        if (p) {
-            if (pinned) cudaFreeHost(p);
-            else cudaFree(p);
-        }
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct cj_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    unsigned* counters = nullptr;  // device work-queue counters
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
-    uint64_t launches = 0;
-    std::mutex mu;
-    Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;
-    cj_ctx() {
-        h_src.pinned = h_dst.pinned = h_desc.pinned = true;
-    }
-};
 
 extern "C" {
 
@@ -156,8 +79,7 @@ void cj_ctx_destroy(cj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->d_src.release(); c->d_dst.release(); c->d_desc.release();
-    c->h_src.release(); c->h_dst.release(); c->h_desc.release();
+    c->release_all();
     if (c->counters) cudaFree(c->counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -214,6 +136,7 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, c->counters, c->sm_count, c->stream);
+        else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, c->counters, c->sm_count, c->stream);
         else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
     } else {
         int accel = params && params->acceleration > 0 ? params->acceleration : 1;
@@ -228,25 +151,6 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         return CJ_E_CUDA;
     }
     return CJ_OK;
-}
-
-static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-
-// Parallel host memcpy over units (gather into / scatter out of the pinned staging buffers).
-template <class F>
-static void parallel_units(size_t n, size_t bytes, F&& f) {
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = bytes < ((size_t)8 << 20) ? 1 : std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, n});
-    if (nt <= 1) {
-        for (size_t i = 0; i < n; i++) f(i);
-        return;
-    }
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nt; t++)
-        th.emplace_back([=, &f]() {
-            for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; i++) f(i);
-        });
-    for (auto& t : th) t.join();
 }
 
 // Batch whose payload lives in host memory: stage -> H2D -> kernel -> D2H -> unstage.
@@ -276,7 +180,7 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
         s_bytes = (size_t)(s_hi - s_lo);
     } else {
         size_t acc = 0;
-        for (size_t i = 0; i < n; i++) { so[i] = acc; acc += align16((size_t)bt->src_len[i]); }
+        for (size_t i = 0; i < n; i++) { so[i] = acc; acc += cj_align16((size_t)bt->src_len[i]); }
         s_bytes = acc;
     }
     if (d_span) {
@@ -284,7 +188,7 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
         d_bytes = (size_t)(d_hi - d_lo);
     } else {
         size_t acc = 0;
-        for (size_t i = 0; i < n; i++) { doff[i] = acc; acc += align16((size_t)bt->dst_cap[i]); }
+        for (size_t i = 0; i < n; i++) { doff[i] = acc; acc += cj_align16((size_t)bt->dst_cap[i]); }
         d_bytes = acc;
     }
     int rc;
@@ -309,7 +213,7 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
     } else {
         if ((rc = c->h_src.ensure(s_bytes + 16))) return rc;
         uint8_t* stage = (uint8_t*)c->h_src.p;
-        parallel_units(n, s_bytes, [&](size_t i) { memcpy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
+        cj_parallel_units(n, s_bytes, [&](size_t i) { memcpy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
         CUDA_TRY(cudaMemcpyAsync(c->d_src.p, stage, s_bytes, cudaMemcpyHostToDevice, c->stream));
     }
 
@@ -348,7 +252,7 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
         uint8_t* stage = (uint8_t*)c->h_dst.p;
         if (last_end) CUDA_TRY(cudaMemcpyAsync(stage, c->d_dst.p, last_end, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        parallel_units(n, last_end, [&](size_t i) { if (dl[i]) memcpy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); });
+        cj_parallel_units(n, last_end, [&](size_t i) { if (dl[i]) memcpy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); });
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(bt->dst_len, hq + 4 * n, n * 8);
@@ -364,9 +268,10 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     }
     std::lock_guard<std::mutex> g(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
-    if (codec == CJ_SNAPPY_FRAMED || codec == CJ_LZ4_FRAME || codec == CJ_ZSTD)
+    if (codec == CJ_SNAPPY_FRAMED || codec == CJ_ZSTD || (codec == CJ_LZ4_FRAME && compress))
         return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
-    if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
+    // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
+    if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
     if (where == CJ_DEVICE) {
         if (bt->n > 0xffffffffull) { cj_set_error("too many units"); return CJ_E_INVALID_ARG; }
         cj::Batch b;
@@ -382,11 +287,6 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
 // Entry used by frames.cu for the block payloads it has already placed in device memory.
 int cj_run_device_batch(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params) {
     return run_device(c, codec, compress, b, params);
-}
-cudaStream_t cj_ctx_stream(cj_ctx* c) { return c->stream; }
-int cj_ctx_sm_count(cj_ctx* c) { return c->sm_count; }
-int cj_run_host_batch(cj_ctx* c, int codec, bool compress, int where, const cj_batch* bt, const cj_params* params) {
-    return run_host(c, codec, compress, where, bt, params);
 }
 
 extern "C" {
@@ -440,7 +340,7 @@ int cj_synth_blocks(cj_ctx* c, cj_mem where, void* dst, size_t n_blocks, size_t 
     }
     // host generator: same function, used for CPU baselines and parity fixtures (no ctx needed)
     uint8_t* out = (uint8_t*)dst;
-    parallel_units(n_blocks, n_blocks * block_len, [&](size_t i) { cj::synth_block(out + i * block_len, block_len, seed, first_index + i); });
+    cj_parallel_units(n_blocks, n_blocks * block_len, [&](size_t i) { cj::synth_block(out + i * block_len, block_len, seed, first_index + i); });
     return CJ_OK;
 }
 

@@ -1,0 +1,848 @@
+// frames.cu — frame containers around the block codecs (sm_100a + host plumbing).
+//
+//   snappy framing format  : cramjam.snappy.compress/decompress(_into)  reference src/snappy.rs:22-42,81-90
+//                            (snap::read::FrameEncoder / FrameDecoder)
+//   LZ4 frame (LZ4F)       : cramjam.lz4.compress/decompress(_into)     reference src/lz4.rs:27-65 (lz4::Encoder/Decoder)
+//
+// Snappy framed streams are cut into their (independent, <= 64 KiB) chunks on the host — a walk
+// over 4-byte chunk headers, no payload byte is interpreted on the CPU — and every chunk becomes
+// one unit of the batched raw-block kernels; masked CRC-32C of each chunk is computed on the device
+// and checked / emitted.  LZ4 frames are decoded by one warp per frame walking the blocks on the
+// device (linked blocks depend on the previous 64 KiB of output, so blocks of one frame run in
+// order); XXH32 header / block / content checksums are verified in the same kernel.  The encoders
+// emit independent 64 KiB blocks (legal LZ4F), one unit of the block encoder each.
+#include "internal.h"
+#include "lz_decode.cuh"
+
+namespace cj {
+
+// ================================================================================================
+// Checksums on the device
+// ================================================================================================
+#define XP1 2654435761u
+#define XP2 2246822519u
+#define XP3 3266489917u
+#define XP4 668265263u
+#define XP5 374761393u
+
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+template <class LoadByte>
+__host__ __device__ __forceinline__ uint32_t xxh32_generic(LoadByte ld, uint64_t n, uint32_t seed) {
+    uint64_t p = 0;
+    uint32_t h;
+    auto rd = [&](uint64_t q) { return (uint32_t)ld(q) | ((uint32_t)ld(q + 1) << 8) | ((uint32_t)ld(q + 2) << 16) | ((uint32_t)ld(q + 3) << 24); };
+    if (n >= 16) {
+        uint32_t v1 = seed + XP1 + XP2, v2 = seed + XP2, v3 = seed, v4 = seed - XP1;
+        do {
+            v1 = rotl32(v1 + rd(p) * XP2, 13) * XP1;
+            v2 = rotl32(v2 + rd(p + 4) * XP2, 13) * XP1;
+            v3 = rotl32(v3 + rd(p + 8) * XP2, 13) * XP1;
+            v4 = rotl32(v4 + rd(p + 12) * XP2, 13) * XP1;
+            p += 16;
+        } while (p + 16 <= n);
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+    } else {
+        h = seed + XP5;
+    }
+    h += (uint32_t)n;
+    while (p + 4 <= n) { h = rotl32(h + rd(p) * XP3, 17) * XP4; p += 4; }
+    while (p < n) { h = rotl32(h + (uint32_t)ld(p) * XP5, 11) * XP1; p++; }
+    h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+    return h;
+}
+
+// XXH32 of a global-memory range; word loads when the range is 4-byte aligned.
+__device__ uint32_t xxh32_global(const uint8_t* p, uint64_t n) {
+    if (((uintptr_t)p & 3) == 0) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+        uint64_t i = 0;
+        uint32_t h;
+        if (n >= 16) {
+            uint32_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0u - XP1;
+            do {
+                const uint4 q = __ldcg(reinterpret_cast<const uint4*>(w + i));  // 16 B aligned when p is; else falls to scalar path below
+                v1 = rotl32(v1 + q.x * XP2, 13) * XP1;
+                v2 = rotl32(v2 + q.y * XP2, 13) * XP1;
+                v3 = rotl32(v3 + q.z * XP2, 13) * XP1;
+                v4 = rotl32(v4 + q.w * XP2, 13) * XP1;
+                i += 4;
+            } while (i * 4 + 16 <= n);
+            h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+        } else {
+            h = XP5;
+        }
+        h += (uint32_t)n;
+        uint64_t b = i * 4;
+        while (b + 4 <= n) { h = rotl32(h + __ldcg(w + b / 4) * XP3, 17) * XP4; b += 4; }
+        while (b < n) { h = rotl32(h + (uint32_t)__ldcg(p + b) * XP5, 11) * XP1; b++; }
+        h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+        return h;
+    }
+    return xxh32_generic([&](uint64_t q) { return __ldcg(p + q); }, n, 0);
+}
+
+__global__ void xxh32_units_kernel(uint32_t n, const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+                                   uint32_t* __restrict__ out) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const uint8_t* p = base + off[u];
+    if (((uintptr_t)p & 15) == 0) out[u] = xxh32_global(p, len[u]);
+    else out[u] = xxh32_generic([&](uint64_t q) { return __ldcg(p + q); }, len[u], 0);
+}
+
+// CRC-32C (Castagnoli), slicing-by-8 tables built in shared memory by each CTA; one thread per unit.
+__global__ void __launch_bounds__(128) crc32c_units_kernel(uint32_t n, const uint8_t* __restrict__ base, const uint64_t* __restrict__ off,
+                                                           const uint64_t* __restrict__ len, uint32_t* __restrict__ out_masked) {
+    __shared__ uint32_t T[8][256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+        T[0][i] = c;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = T[0][i];
+        for (int t = 1; t < 8; t++) {
+            c = (c >> 8) ^ T[0][c & 0xff];
+            T[t][i] = c;
+        }
+    }
+    __syncthreads();
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const uint8_t* p = base + off[u];
+    uint64_t L = len[u];
+    uint32_t c = 0xFFFFFFFFu;
+    while (L && ((uintptr_t)p & 7)) { c = (c >> 8) ^ T[0][(c ^ __ldcg(p)) & 0xff]; p++; L--; }
+    while (L >= 8) {
+        const uint2 w = __ldcg(reinterpret_cast<const uint2*>(p));
+        const uint32_t lo = w.x ^ c, hi = w.y;
+        c = T[7][lo & 0xff] ^ T[6][(lo >> 8) & 0xff] ^ T[5][(lo >> 16) & 0xff] ^ T[4][lo >> 24] ^ T[3][hi & 0xff] ^ T[2][(hi >> 8) & 0xff] ^
+            T[1][(hi >> 16) & 0xff] ^ T[0][hi >> 24];
+        p += 8;
+        L -= 8;
+    }
+    while (L) { c = (c >> 8) ^ T[0][(c ^ __ldcg(p)) & 0xff]; p++; L--; }
+    c ^= 0xFFFFFFFFu;
+    out_masked[u] = ((c >> 15) | (c << 17)) + 0xa282ead8u;
+}
+
+// ================================================================================================
+// LZ4 frame decode: one warp per frame stream (concatenated + skippable frames included)
+// ================================================================================================
+__device__ __forceinline__ uint32_t rd32g(const uint8_t* p) {
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+}
+
+__device__ int32_t lz4f_decode_stream(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap, uint8_t* smem_warp, int lane,
+                                      uint32_t* produced) {
+    OutRing out;
+    out.init(smem_warp, dst, lane);
+    uint32_t ip = 0;
+    int32_t st = CJ_OK;
+    while (ip < n && st == CJ_OK) {
+        if (n - ip < 4) { st = CJ_ST_TRUNCATED; break; }
+        const uint32_t magic = rd32g(src + ip);
+        if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {  // skippable frame
+            if (n - ip < 8) { st = CJ_ST_TRUNCATED; break; }
+            const uint32_t sz = rd32g(src + ip + 4);
+            if (sz > n - ip - 8) { st = CJ_ST_TRUNCATED; break; }
+            ip += 8 + sz;
+            continue;
+        }
+        if (magic != 0x184D2204u) { st = CJ_ST_HEADER; break; }
+        if (n - ip < 7) { st = CJ_ST_TRUNCATED; break; }
+        const uint32_t flg = __ldg(src + ip + 4), bd = __ldg(src + ip + 5);
+        if ((flg >> 6) != 1 || (flg & 0x02) || (bd & 0x8F)) { st = CJ_ST_HEADER; break; }
+        const bool indep = (flg >> 5) & 1, bsum = (flg >> 4) & 1, csize = (flg >> 3) & 1, csum = (flg >> 2) & 1, dict = flg & 1;
+        const uint32_t bid = (bd >> 4) & 7;
+        if (bid < 4) { st = CJ_ST_HEADER; break; }
+        const uint32_t bmax = 1u << (8 + 2 * bid);
+        const uint32_t dlen = 2 + (csize ? 8 : 0) + (dict ? 4 : 0);
+        if (n - ip < 4 + dlen + 1) { st = CJ_ST_TRUNCATED; break; }
+        const uint8_t* desc = src + ip + 4;
+        if (((xxh32_generic([&](uint64_t q) { return __ldg(desc + q); }, dlen, 0) >> 8) & 0xff) != __ldg(desc + dlen)) { st = CJ_ST_CHECKSUM; break; }
+        uint64_t content_size = 0;
+        if (csize) content_size = (uint64_t)rd32g(desc + 2) | ((uint64_t)rd32g(desc + 6) << 32);
+        if (dict) { st = CJ_ST_UNSUPPORTED; break; }
+        ip += 4 + dlen + 1;
+        const uint32_t frame_start = out.op;
+        for (;;) {
+            if (n - ip < 4) { st = CJ_ST_TRUNCATED; break; }
+            const uint32_t bs = rd32g(src + ip);
+            ip += 4;
+            if (bs == 0) break;
+            const bool stored = bs >> 31;
+            const uint32_t blen = bs & 0x7FFFFFFFu;
+            if (blen > bmax) { st = CJ_ST_CORRUPT; break; }
+            if (blen > n - ip) { st = CJ_ST_TRUNCATED; break; }
+            if (bsum) {
+                if (n - ip - blen < 4) { st = CJ_ST_TRUNCATED; break; }
+                uint32_t h = 0;
+                const uint8_t* bp = src + ip;
+                if (lane == 0) h = xxh32_generic([&](uint64_t q) { return __ldg(bp + q); }, blen, 0);
+                h = __shfl_sync(FULL, h, 0);
+                if (h != rd32g(src + ip + blen)) { st = CJ_ST_CHECKSUM; break; }
+            }
+            if (stored) {
+                if (blen > cap - out.op) { st = CJ_ST_DST_SMALL; break; }
+                out.put_literals(src + ip, blen);
+            } else {
+                if (blen == 0) { st = CJ_ST_EMPTY; break; }
+                out.base = indep ? out.op : frame_start;
+                const uint32_t room = min(cap - out.op, bmax);
+                st = decode_stream<CJ_LZ4_BLOCK, true>(src + ip, blen, 0, out.op + room, out, smem_warp, lane);
+                if (st != CJ_OK) {
+                    if (st == CJ_ST_DST_SMALL && room == bmax) st = CJ_ST_CORRUPT;  // block larger than the frame's block size
+                    break;
+                }
+            }
+            ip += blen + (bsum ? 4 : 0);
+        }
+        if (st != CJ_OK) break;
+        if (csum) {
+            if (n - ip < 4) { st = CJ_ST_TRUNCATED; break; }
+            out.flush_to(out.op, true);
+            uint32_t h = 0;
+            if (lane == 0) h = xxh32_global(dst + frame_start, out.op - frame_start);
+            h = __shfl_sync(FULL, h, 0);
+            if (h != rd32g(src + ip)) { st = CJ_ST_CHECKSUM; break; }
+            ip += 4;
+        }
+        if (csize && content_size != (uint64_t)(out.op - frame_start)) { st = CJ_ST_LEN_MISMATCH; break; }
+    }
+    out.finish();
+    *produced = out.op;
+    return st;
+}
+
+__global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz4f_decode_kernel(Batch b, unsigned* __restrict__ counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* smem_warp = smem + (size_t)warp * DEC_SMEM_WARP;
+    for (;;) {
+        const uint32_t u = next_unit(counter, lane);
+        if (u >= b.n) break;
+        const uint64_t slen = b.src_len[u], dcap = b.dst_cap[u];
+        uint32_t produced = 0;
+        int32_t st;
+        if (slen > MAX_UNIT) st = CJ_ST_TOO_BIG;
+        else st = lz4f_decode_stream(b.src_base + b.src_off[u], (uint32_t)slen, b.dst_base + b.dst_off[u], dcap > MAX_UNIT ? MAX_UNIT : (uint32_t)dcap,
+                                     smem_warp, lane, &produced);
+        if (lane == 0) {
+            b.dst_len[u] = st == CJ_OK ? produced : 0;
+            b.status[u] = st;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)DEC_SMEM_WARP * DEC_WARPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(lz4f_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    int grid = sm_count * CJ_DEC_CTAS;
+    const int need = (int)((b.n + DEC_WARPS - 1) / DEC_WARPS);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    lz4f_decode_kernel<<<grid, DEC_WARPS * 32, smem, stream>>>(b, counter);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// Host plumbing
+// ================================================================================================
+namespace {
+
+inline uint32_t h_rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline void h_wr32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+inline uint32_t h_xxh32(const uint8_t* p, size_t n) { return xxh32_generic([&](uint64_t q) { return p[q]; }, n, 0); }
+
+// A flat list of device work items referring to one device source arena and one device destination arena.
+struct Items {
+    std::vector<uint64_t> so, sl, dof, dc;
+    size_t size() const { return so.size(); }
+    void add(uint64_t a, uint64_t b, uint64_t c, uint64_t d) { so.push_back(a); sl.push_back(b); dof.push_back(c); dc.push_back(d); }
+};
+
+// Uploads item descriptors; returns device pointers inside ctx->f_ddesc (layout: so | sl | dof | dc | dl | st(i32) | aux(u32)).
+struct DevItems {
+    uint64_t *so, *sl, *dof, *dc, *dl;
+    int32_t* st;
+    uint32_t* aux;
+    uint64_t* h;  // pinned host mirror, same layout
+    size_t n;
+};
+
+int upload_items(cj_ctx* c, const Items& it, Scratch& dsc, Scratch& hsc, DevItems* out) {
+    const size_t n = it.size();
+    const size_t bytes = n * (5 * 8 + 4 + 4) + 64;
+    int rc;
+    if ((rc = dsc.ensure(bytes))) return rc;
+    if ((rc = hsc.ensure(bytes))) return rc;
+    uint64_t* h = (uint64_t*)hsc.p;
+    if (n) {
+        memcpy(h, it.so.data(), n * 8);
+        memcpy(h + n, it.sl.data(), n * 8);
+        memcpy(h + 2 * n, it.dof.data(), n * 8);
+        memcpy(h + 3 * n, it.dc.data(), n * 8);
+        CUDA_TRY(cudaMemcpyAsync(dsc.p, h, n * 32, cudaMemcpyHostToDevice, c->stream));
+    }
+    uint64_t* d = (uint64_t*)dsc.p;
+    out->so = d; out->sl = d + n; out->dof = d + 2 * n; out->dc = d + 3 * n; out->dl = d + 4 * n;
+    out->st = (int32_t*)(d + 5 * n);
+    out->aux = (uint32_t*)(out->st + n);
+    out->h = h;
+    out->n = n;
+    return CJ_OK;
+}
+
+int fetch_results(cj_ctx* c, const DevItems& d) {  // dl | st | aux back to the pinned mirror
+    if (d.n) CUDA_TRY(cudaMemcpyAsync(d.h + 4 * d.n, d.dl, d.n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CJ_OK;
+}
+
+// Copies every unit's source bytes into a device arena (16-byte aligned starts); base[i] = arena offset of unit i.
+int upload_units(cj_ctx* c, const cj_batch* bt, int where, std::vector<uint64_t>& base, size_t extra_tail = 64) {
+    const size_t n = bt->n;
+    base.resize(n);
+    size_t acc = 0;
+    for (size_t i = 0; i < n; i++) { base[i] = acc; acc += cj_align16((size_t)bt->src_len[i]); }
+    int rc;
+    if ((rc = c->f_dsrc.ensure(acc + extra_tail))) return rc;
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    if (where == CJ_PINNED) {
+        for (size_t i = 0; i < n; i++)
+            if (bt->src_len[i]) CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->f_dsrc.p + base[i], hs + bt->src_off[i], (size_t)bt->src_len[i], cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if ((rc = c->f_hsrc.ensure(acc + extra_tail))) return rc;
+        uint8_t* stage = (uint8_t*)c->f_hsrc.p;
+        cj_parallel_units(n, acc, [&](size_t i) { memcpy(stage + base[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
+        if (acc) CUDA_TRY(cudaMemcpyAsync(c->f_dsrc.p, stage, acc, cudaMemcpyHostToDevice, c->stream));
+    }
+    return CJ_OK;
+}
+
+// Copies produced bytes of every OK unit from the device destination arena back to the caller.
+int download_units(cj_ctx* c, const cj_batch* bt, int where, const std::vector<uint64_t>& dbase, size_t arena_bytes) {
+    const size_t n = bt->n;
+    uint8_t* hd = (uint8_t*)bt->dst_base;
+    if (where == CJ_PINNED) {
+        for (size_t i = 0; i < n; i++)
+            if (bt->status[i] == CJ_OK && bt->dst_len[i])
+                CUDA_TRY(cudaMemcpyAsync(hd + bt->dst_off[i], (uint8_t*)c->f_ddst.p + dbase[i], (size_t)bt->dst_len[i], cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    } else {
+        int rc;
+        if ((rc = c->f_hdst.ensure(arena_bytes + 64))) return rc;
+        if (arena_bytes) CUDA_TRY(cudaMemcpyAsync(c->f_hdst.p, c->f_ddst.p, arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const uint8_t* stage = (const uint8_t*)c->f_hdst.p;
+        cj_parallel_units(n, arena_bytes, [&](size_t i) {
+            if (bt->status[i] == CJ_OK && bt->dst_len[i]) memcpy(hd + bt->dst_off[i], stage + dbase[i], (size_t)bt->dst_len[i]);
+        });
+    }
+    return CJ_OK;
+}
+
+int launch_crc(cj_ctx* c, uint32_t n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* out) {
+    if (!n) return CJ_OK;
+    crc32c_units_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(n, base, off, len, out);
+    c->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return CJ_OK;
+}
+
+int launch_xxh32(cj_ctx* c, uint32_t n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* out) {
+    if (!n) return CJ_OK;
+    xxh32_units_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(n, base, off, len, out);
+    c->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return CJ_OK;
+}
+
+int copy_units(cj_ctx* c, uint32_t n, const uint8_t* sb, const uint64_t* so, const uint64_t* len, uint8_t* db, const uint64_t* dof) {
+    if (!n) return CJ_OK;
+    cudaError_t e = launch_copy_units(n, sb, so, len, db, dof, c->sm_count, c->stream);
+    c->launches += 1;
+    if (e != cudaSuccess) { cj_set_error("copy_units launch failed: %s", cudaGetErrorString(e)); return CJ_E_CUDA; }
+    return CJ_OK;
+}
+
+// ---- snappy framing: host walk over chunk headers ---------------------------------------------
+struct SnChunk { uint64_t body_off; uint32_t body_len; uint32_t ulen; uint32_t crc; bool compressed; };
+
+int32_t snappy_uvarint(const uint8_t* p, size_t n, uint64_t* v) {  // returns header bytes or 0
+    uint64_t r = 0;
+    for (int i = 0; i < 5 && (size_t)i < n; i++) {
+        r |= (uint64_t)(p[i] & 0x7f) << (7 * i);
+        if (!(p[i] & 0x80)) { *v = r; return i + 1; }
+    }
+    return 0;
+}
+
+int32_t snappy_frame_walk(const uint8_t* s, size_t n, std::vector<SnChunk>* chunks, uint64_t* total) {
+    size_t p = 0;
+    bool seen = false;
+    uint64_t tot = 0;
+    while (p < n) {
+        if (n - p < 4) return CJ_ST_TRUNCATED;
+        const uint8_t type = s[p];
+        const size_t len = (size_t)s[p + 1] | ((size_t)s[p + 2] << 8) | ((size_t)s[p + 3] << 16);
+        p += 4;
+        if (len > n - p) return CJ_ST_TRUNCATED;
+        if (!seen && type != 0xff) return CJ_ST_HEADER;
+        if (type == 0xff) {
+            if (len != 6 || memcmp(s + p, "sNaPpY", 6) != 0) return CJ_ST_HEADER;
+            seen = true;
+        } else if (type == 0x00 || type == 0x01) {
+            if (len < 4) return CJ_ST_CORRUPT;
+            SnChunk c;
+            c.crc = h_rd32(s + p);
+            c.body_off = p + 4;
+            c.body_len = (uint32_t)(len - 4);
+            c.compressed = type == 0x00;
+            if (c.compressed) {
+                uint64_t u;
+                if (c.body_len == 0) return CJ_ST_EMPTY;
+                if (!snappy_uvarint(s + p + 4, c.body_len, &u)) return CJ_ST_HEADER;
+                if (u > 0xFFFFFFFFull) return CJ_ST_TOO_BIG;
+                if (u > 65536) return CJ_ST_CORRUPT;
+                c.ulen = (uint32_t)u;
+            } else {
+                if (c.body_len > 65536) return CJ_ST_CORRUPT;
+                c.ulen = c.body_len;
+            }
+            tot += c.ulen;
+            if (chunks) chunks->push_back(c);
+        } else if (type < 0x80) {
+            return CJ_ST_CORRUPT;  // 0x02-0x7f reserved unskippable
+        }
+        p += len;
+    }
+    *total = tot;
+    return CJ_OK;
+}
+
+int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
+    const size_t n = bt->n;
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    std::vector<uint64_t> sbase, dbase(n);
+    std::vector<std::vector<SnChunk>> chunks(n);
+    std::vector<uint64_t> total(n, 0);
+    size_t dacc = 0;
+    for (size_t i = 0; i < n; i++) {
+        bt->status[i] = snappy_frame_walk(hs + bt->src_off[i], (size_t)bt->src_len[i], &chunks[i], &total[i]);
+        bt->dst_len[i] = 0;
+        if (bt->status[i] == CJ_OK && total[i] > bt->dst_cap[i]) bt->status[i] = CJ_ST_DST_SMALL;
+        dbase[i] = dacc;
+        if (bt->status[i] == CJ_OK) dacc += cj_align16((size_t)total[i]);
+    }
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    if ((rc = c->f_ddst.ensure(dacc + 64))) return rc;
+    Items comp, stored, all;
+    std::vector<uint32_t> want_crc, owner;      // per entry of `all`
+    std::vector<int64_t> comp_idx;              // per entry of `all`: index into `comp`, or -1 for a stored chunk
+    for (size_t i = 0; i < n; i++) {
+        if (bt->status[i] != CJ_OK) continue;
+        uint64_t d = dbase[i];
+        for (const SnChunk& ch : chunks[i]) {
+            if (ch.compressed) { comp_idx.push_back((int64_t)comp.size()); comp.add(sbase[i] + ch.body_off, ch.body_len, d, ch.ulen); }
+            else { comp_idx.push_back(-1); stored.add(sbase[i] + ch.body_off, ch.body_len, d, ch.ulen); }
+            all.add(d, ch.ulen, 0, 0);
+            want_crc.push_back(ch.crc);
+            owner.push_back((uint32_t)i);
+            d += ch.ulen;
+        }
+    }
+    // compressed chunks -> raw block decoder; stored chunks -> device copy; then CRC of every chunk
+    Scratch &dd = c->f_ddesc, &hd = c->f_hdesc;
+    // three descriptor groups share the scratch: carve them out of one allocation
+    const size_t per = 48 + 8;
+    const size_t need = (comp.size() + stored.size() + all.size()) * per + 3 * 64;
+    if ((rc = dd.ensure(need))) return rc;
+    if ((rc = hd.ensure(need))) return rc;
+    auto carve = [&](const Items& it, size_t byte_off, DevItems* out) -> int {
+        Scratch ds, hs2;
+        ds.p = (uint8_t*)dd.p + byte_off; ds.cap = dd.cap - byte_off;
+        hs2.p = (uint8_t*)hd.p + byte_off; hs2.cap = hd.cap - byte_off; hs2.pinned = true;
+        int r = upload_items(c, it, ds, hs2, out);
+        ds.p = nullptr; hs2.p = nullptr;  // not owned
+        return r;
+    };
+    DevItems dcomp, dstored, dall;
+    size_t o0 = 0, o1 = cj_align16(comp.size() * per + 16), o2 = o1 + cj_align16(stored.size() * per + 16);
+    if ((rc = carve(comp, o0, &dcomp))) return rc;
+    if ((rc = carve(stored, o1, &dstored))) return rc;
+    if ((rc = carve(all, o2, &dall))) return rc;
+    if (comp.size()) {
+        Batch b;
+        b.n = (uint32_t)comp.size();
+        b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = dcomp.so; b.src_len = dcomp.sl;
+        b.dst_base = (uint8_t*)c->f_ddst.p; b.dst_off = dcomp.dof; b.dst_cap = dcomp.dc; b.dst_len = dcomp.dl; b.status = dcomp.st;
+        if ((rc = cj_run_device_batch(c, CJ_SNAPPY_RAW, false, b, nullptr))) return rc;
+    }
+    if ((rc = copy_units(c, (uint32_t)stored.size(), (const uint8_t*)c->f_dsrc.p, dstored.so, dstored.sl, (uint8_t*)c->f_ddst.p, dstored.dof))) return rc;
+    if ((rc = launch_crc(c, (uint32_t)all.size(), (const uint8_t*)c->f_ddst.p, dall.so, dall.sl, dall.aux))) return rc;
+    if ((rc = fetch_results(c, dcomp))) return rc;
+    if ((rc = fetch_results(c, dall))) return rc;
+    // fold chunk results into unit results (first failure in stream order wins)
+    {
+        const uint64_t* cdl = dcomp.h + 4 * dcomp.n;
+        const int32_t* cst = (const int32_t*)(dcomp.h + 5 * dcomp.n);
+        const uint32_t* got = (const uint32_t*)((const int32_t*)(dall.h + 5 * dall.n) + dall.n);
+        std::vector<int32_t> ust(n, CJ_OK);
+        for (size_t k = 0; k < all.size(); k++) {
+            const uint32_t u = owner[k];
+            int32_t st = CJ_OK;
+            if (comp_idx[k] >= 0) {
+                const size_t ci = (size_t)comp_idx[k];
+                st = cst[ci];
+                if (st == CJ_OK && cdl[ci] != all.sl[k]) st = CJ_ST_LEN_MISMATCH;
+            }
+            if (st == CJ_OK && got[k] != want_crc[k]) st = CJ_ST_CHECKSUM;
+            if (ust[u] == CJ_OK && st != CJ_OK) ust[u] = st;
+        }
+        for (size_t i = 0; i < n; i++)
+            if (bt->status[i] == CJ_OK) {
+                bt->status[i] = ust[i];
+                bt->dst_len[i] = ust[i] == CJ_OK ? total[i] : 0;
+            }
+    }
+    return download_units(c, bt, where, dbase, dacc);
+}
+
+int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
+    const size_t n = bt->n;
+    static const uint8_t STREAM_ID[10] = {0xff, 0x06, 0x00, 0x00, 's', 'N', 'a', 'P', 'p', 'Y'};
+    std::vector<uint64_t> sbase;
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    const size_t slot = cj_align16(32 + 65536 + 65536 / 6);
+    Items ch;  // one item per 64 KiB chunk: raw chunk -> slot
+    std::vector<uint32_t> owner;
+    for (size_t i = 0; i < n; i++) {
+        bt->status[i] = CJ_OK;
+        bt->dst_len[i] = 0;
+        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536) {
+            const uint64_t L = std::min<uint64_t>(65536, bt->src_len[i] - p);
+            ch.add(sbase[i] + p, L, ch.size() * slot, slot);
+            owner.push_back((uint32_t)i);
+        }
+    }
+    const size_t nc = ch.size();
+    if ((rc = c->f_dtmp.ensure(nc * slot + 64))) return rc;
+    DevItems dch;
+    if ((rc = upload_items(c, ch, c->f_ddesc, c->f_hdesc, &dch))) return rc;
+    if (nc) {
+        Batch b;
+        b.n = (uint32_t)nc;
+        b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = dch.so; b.src_len = dch.sl;
+        b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = dch.dof; b.dst_cap = dch.dc; b.dst_len = dch.dl; b.status = dch.st;
+        if ((rc = cj_run_device_batch(c, CJ_SNAPPY_RAW, true, b, nullptr))) return rc;
+        if ((rc = launch_crc(c, (uint32_t)nc, (const uint8_t*)c->f_dsrc.p, dch.so, dch.sl, dch.aux))) return rc;
+    }
+    if ((rc = fetch_results(c, dch))) return rc;
+    const uint64_t* clen = dch.h + 4 * nc;
+    const int32_t* cst = (const int32_t*)(dch.h + 5 * nc);
+    const uint32_t* crc = (const uint32_t*)(cst + nc);
+    // layout of every output stream; header bytes are assembled on the host (framing only), bodies are spliced on the device
+    std::vector<uint64_t> dbase(n), total(n, 0);
+    size_t dacc = 0;
+    Items body_comp, body_raw, hdr;
+    std::vector<uint8_t> hdr_bytes;
+    hdr_bytes.reserve(10 * n + 8 * nc + 64);
+    size_t k = 0;
+    for (size_t i = 0; i < n; i++) {
+        dbase[i] = dacc;
+        if (bt->status[i] != CJ_OK) continue;
+        uint64_t pos = 10;
+        hdr.add(hdr_bytes.size(), 10, dacc, 0);
+        hdr_bytes.insert(hdr_bytes.end(), STREAM_ID, STREAM_ID + 10);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536, k++) {
+            const uint64_t L = ch.sl[k];
+            if (cst[k] != CJ_OK) { bt->status[i] = cst[k]; }
+            const bool use_comp = clen[k] < L - L / 8;  // snap: keep the compressed form only if it saves >= 12.5 %
+            const uint64_t body = use_comp ? clen[k] : L;
+            uint8_t h8[8];
+            h8[0] = use_comp ? 0x00 : 0x01;
+            const uint64_t cl = body + 4;
+            h8[1] = (uint8_t)cl; h8[2] = (uint8_t)(cl >> 8); h8[3] = (uint8_t)(cl >> 16);
+            h_wr32(h8 + 4, crc[k]);
+            hdr.add(hdr_bytes.size(), 8, dacc + pos, 0);
+            hdr_bytes.insert(hdr_bytes.end(), h8, h8 + 8);
+            if (use_comp) body_comp.add(ch.dof[k], body, dacc + pos + 8, 0);
+            else body_raw.add(ch.so[k], body, dacc + pos + 8, 0);
+            pos += 8 + body;
+        }
+        total[i] = pos;
+        if (bt->status[i] == CJ_OK && pos > bt->dst_cap[i]) bt->status[i] = CJ_ST_DST_SMALL;
+        dacc += cj_align16((size_t)pos);
+    }
+    if ((rc = c->f_ddst.ensure(dacc + hdr_bytes.size() + 128))) return rc;
+    // header blob rides at the end of the destination arena
+    const size_t blob_off = dacc;
+    if (!hdr_bytes.empty()) {
+        if ((rc = c->f_hdst.ensure(hdr_bytes.size() + 64))) return rc;
+        memcpy(c->f_hdst.p, hdr_bytes.data(), hdr_bytes.size());
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->f_ddst.p + blob_off, c->f_hdst.p, hdr_bytes.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    auto splice = [&](const Items& it, const uint8_t* sb, uint64_t sadd) -> int {
+        if (!it.size()) return CJ_OK;
+        Items t = it;
+        for (auto& v : t.so) v += sadd;
+        DevItems d;
+        int r = upload_items(c, t, c->f_ddesc, c->f_hdesc, &d);
+        if (r) return r;
+        r = copy_units(c, (uint32_t)t.size(), sb, d.so, d.sl, (uint8_t*)c->f_ddst.p, d.dof);
+        if (r) return r;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // descriptor scratch is reused by the next splice
+        return CJ_OK;
+    };
+    if ((rc = splice(hdr, (const uint8_t*)c->f_ddst.p, blob_off))) return rc;
+    if ((rc = splice(body_comp, (const uint8_t*)c->f_dtmp.p, 0))) return rc;
+    if ((rc = splice(body_raw, (const uint8_t*)c->f_dsrc.p, 0))) return rc;
+    for (size_t i = 0; i < n; i++) bt->dst_len[i] = bt->status[i] == CJ_OK ? total[i] : 0;
+    return download_units(c, bt, where, dbase, dacc);
+}
+
+// ---- LZ4 frame compress: independent 64 KiB blocks + content checksum --------------------------------
+int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* params) {
+    (void)params;  // every level maps to the greedy block encoder (LZ4HC-class levels are a "next" row)
+    const size_t n = bt->n;
+    std::vector<uint64_t> sbase;
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    const size_t slot = cj_align16(65536 + 65536 / 255 + 16);
+    Items ch, whole;
+    for (size_t i = 0; i < n; i++) {
+        bt->status[i] = CJ_OK;
+        bt->dst_len[i] = 0;
+        whole.add(sbase[i], bt->src_len[i], 0, 0);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536) ch.add(sbase[i] + p, std::min<uint64_t>(65536, bt->src_len[i] - p), ch.size() * slot, slot);
+    }
+    const size_t nc = ch.size();
+    if ((rc = c->f_dtmp.ensure(nc * slot + 64))) return rc;
+    // content checksums (one thread per frame) while the block encoder runs
+    DevItems dwhole;
+    Scratch& dd = c->f_ddesc; Scratch& hd = c->f_hdesc;
+    const size_t per = 48 + 8;
+    const size_t need = (nc + n) * per + 2 * 64;
+    if ((rc = dd.ensure(need))) return rc;
+    if ((rc = hd.ensure(need))) return rc;
+    auto carve = [&](const Items& it, size_t byte_off, DevItems* out) -> int {
+        Scratch ds, hs2;
+        ds.p = (uint8_t*)dd.p + byte_off; ds.cap = dd.cap - byte_off;
+        hs2.p = (uint8_t*)hd.p + byte_off; hs2.cap = hd.cap - byte_off; hs2.pinned = true;
+        int r = upload_items(c, it, ds, hs2, out);
+        ds.p = nullptr; hs2.p = nullptr;
+        return r;
+    };
+    DevItems dch;
+    if ((rc = carve(ch, 0, &dch))) return rc;
+    if ((rc = carve(whole, cj_align16(nc * per + 16), &dwhole))) return rc;
+    if (nc) {
+        Batch b;
+        b.n = (uint32_t)nc;
+        b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = dch.so; b.src_len = dch.sl;
+        b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = dch.dof; b.dst_cap = dch.dc; b.dst_len = dch.dl; b.status = dch.st;
+        if ((rc = cj_run_device_batch(c, CJ_LZ4_BLOCK, true, b, nullptr))) return rc;
+    }
+    if ((rc = launch_xxh32(c, (uint32_t)n, (const uint8_t*)c->f_dsrc.p, dwhole.so, dwhole.sl, dwhole.aux))) return rc;
+    if ((rc = fetch_results(c, dch))) return rc;
+    if ((rc = fetch_results(c, dwhole))) return rc;
+    const uint64_t* clen = dch.h + 4 * nc;
+    const int32_t* cst = (const int32_t*)(dch.h + 5 * nc);
+    const uint32_t* content_xxh = (const uint32_t*)((const int32_t*)(dwhole.h + 5 * n) + n);
+    std::vector<uint64_t> dbase(n), total(n, 0);
+    Items body_comp, body_raw, hdr;
+    std::vector<uint8_t> hb;
+    size_t dacc = 0, k = 0;
+    for (size_t i = 0; i < n; i++) {
+        dbase[i] = dacc;
+        uint8_t fh[7];
+        h_wr32(fh, 0x184D2204u);
+        fh[4] = 0x40 | 0x20 | 0x04;  // version 01, independent blocks, content checksum
+        fh[5] = 0x40;                // 64 KiB blocks
+        fh[6] = (uint8_t)(h_xxh32(fh + 4, 2) >> 8);
+        hdr.add(hb.size(), 7, dacc, 0);
+        hb.insert(hb.end(), fh, fh + 7);
+        uint64_t pos = 7;
+        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536, k++) {
+            const uint64_t L = ch.sl[k];
+            if (cst[k] != CJ_OK) bt->status[i] = cst[k];
+            const bool use_comp = clen[k] < L;
+            const uint64_t body = use_comp ? clen[k] : L;
+            uint8_t b4[4];
+            h_wr32(b4, (uint32_t)body | (use_comp ? 0u : 0x80000000u));
+            hdr.add(hb.size(), 4, dacc + pos, 0);
+            hb.insert(hb.end(), b4, b4 + 4);
+            if (use_comp) body_comp.add(ch.dof[k], body, dacc + pos + 4, 0);
+            else body_raw.add(ch.so[k], body, dacc + pos + 4, 0);
+            pos += 4 + body;
+        }
+        uint8_t tail[8];
+        h_wr32(tail, 0);
+        h_wr32(tail + 4, content_xxh[i]);
+        hdr.add(hb.size(), 8, dacc + pos, 0);
+        hb.insert(hb.end(), tail, tail + 8);
+        pos += 8;
+        total[i] = pos;
+        if (bt->status[i] == CJ_OK && pos > bt->dst_cap[i]) bt->status[i] = CJ_ST_DST_SMALL;
+        dacc += cj_align16((size_t)pos);
+    }
+    if ((rc = c->f_ddst.ensure(dacc + hb.size() + 128))) return rc;
+    const size_t blob_off = dacc;
+    if ((rc = c->f_hdst.ensure(hb.size() + 64))) return rc;
+    memcpy(c->f_hdst.p, hb.data(), hb.size());
+    CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->f_ddst.p + blob_off, c->f_hdst.p, hb.size(), cudaMemcpyHostToDevice, c->stream));
+    auto splice = [&](const Items& it, const uint8_t* sb, uint64_t sadd) -> int {
+        if (!it.size()) return CJ_OK;
+        Items t = it;
+        for (auto& v : t.so) v += sadd;
+        DevItems d;
+        int r = upload_items(c, t, c->f_ddesc, c->f_hdesc, &d);
+        if (r) return r;
+        r = copy_units(c, (uint32_t)t.size(), sb, d.so, d.sl, (uint8_t*)c->f_ddst.p, d.dof);
+        if (r) return r;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return CJ_OK;
+    };
+    if ((rc = splice(hdr, (const uint8_t*)c->f_ddst.p, blob_off))) return rc;
+    if ((rc = splice(body_comp, (const uint8_t*)c->f_dtmp.p, 0))) return rc;
+    if ((rc = splice(body_raw, (const uint8_t*)c->f_dsrc.p, 0))) return rc;
+    for (size_t i = 0; i < n; i++) bt->dst_len[i] = bt->status[i] == CJ_OK ? total[i] : 0;
+    return download_units(c, bt, where, dbase, dacc);
+}
+
+}  // namespace
+
+int zstd_decompress_host(cj_ctx* c, int where, const cj_batch* bt);  // zstd_decode.cu
+
+int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
+    if (where == CJ_DEVICE) {
+        cj_set_error("frame containers (codec %d) take host-visible input: pass CJ_HOST or CJ_PINNED", codec);
+        return CJ_E_INVALID_ARG;
+    }
+    if (bt->n == 0) return CJ_OK;
+    if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_decompress(c, where, bt);
+    if (codec == CJ_ZSTD) return zstd_decompress_host(c, where, bt);
+    cj_set_error("unknown frame codec %d", codec);
+    return CJ_E_INVALID_ARG;
+}
+
+int frames_compress(cj_ctx* c, int codec, int where, const cj_batch* bt, const cj_params* params) {
+    if (where == CJ_DEVICE) {
+        cj_set_error("frame containers (codec %d) produce host-visible output: pass CJ_HOST or CJ_PINNED", codec);
+        return CJ_E_INVALID_ARG;
+    }
+    if (bt->n == 0) return CJ_OK;
+    if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_compress(c, where, bt);
+    if (codec == CJ_LZ4_FRAME) return lz4f_compress(c, where, bt, params);
+    cj_set_error("codec %d has no encoder in this build (zstd compress is a listed next step)", codec);
+    return CJ_E_INVALID_ARG;
+}
+
+}  // namespace cj
+
+// ================================================================================================
+// Size helpers on HOST memory (header parsing only)
+// ================================================================================================
+static int lz4f_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact) {
+    size_t p = 0, tot = 0;
+    *exact = true;
+    while (p < n) {
+        if (n - p < 4) return CJ_ST_TRUNCATED;
+        uint32_t magic; memcpy(&magic, s + p, 4);
+        if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {
+            if (n - p < 8) return CJ_ST_TRUNCATED;
+            uint32_t sz; memcpy(&sz, s + p + 4, 4);
+            if (sz > n - p - 8) return CJ_ST_TRUNCATED;
+            p += 8 + sz;
+            continue;
+        }
+        if (magic != 0x184D2204u) return CJ_ST_HEADER;
+        if (n - p < 7) return CJ_ST_TRUNCATED;
+        const uint8_t flg = s[p + 4], bd = s[p + 5];
+        const int bid = (bd >> 4) & 7;
+        if ((flg >> 6) != 1 || bid < 4) return CJ_ST_HEADER;
+        const size_t bmax = (size_t)1 << (8 + 2 * bid);
+        const bool bsum = (flg >> 4) & 1, csize = (flg >> 3) & 1, csum = (flg >> 2) & 1, dict = flg & 1;
+        const size_t dlen = 2 + (csize ? 8 : 0) + (dict ? 4 : 0);
+        if (n - p < 4 + dlen + 1) return CJ_ST_TRUNCATED;
+        uint64_t content = 0;
+        if (csize) memcpy(&content, s + p + 6, 8);
+        p += 4 + dlen + 1;
+        size_t frame_tot = 0;
+        for (;;) {
+            if (n - p < 4) return CJ_ST_TRUNCATED;
+            uint32_t bs; memcpy(&bs, s + p, 4);
+            p += 4;
+            if (bs == 0) break;
+            const size_t blen = bs & 0x7FFFFFFFu;
+            if (blen > n - p) return CJ_ST_TRUNCATED;
+            if (bs >> 31) frame_tot += blen;
+            else { frame_tot += std::min(bmax, blen * 255); if (!csize) *exact = false; }
+            p += blen + (bsum ? 4 : 0);
+            if (p > n) return CJ_ST_TRUNCATED;
+        }
+        if (csum) { if (n - p < 4) return CJ_ST_TRUNCATED; p += 4; }
+        tot += csize ? (size_t)content : frame_tot;
+    }
+    *out = tot;
+    return CJ_OK;
+}
+
+int cj_zstd_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact);  // zstd_decode.cu
+
+static int decompressed_bound(cj_codec codec, const void* src, size_t n, size_t* out, bool want_exact) {
+    if (!out || (!src && n)) return CJ_E_INVALID_ARG;
+    const uint8_t* s = (const uint8_t*)src;
+    int32_t st = CJ_OK;
+    bool exact = true;
+    switch (codec) {
+    case CJ_SNAPPY_RAW: {
+        if (n == 0) { *out = 0; return CJ_OK; }  // snap::raw::decompress_len(b"") == Ok(0)
+        uint64_t v;
+        if (!cj::snappy_uvarint(s, n, &v)) st = CJ_ST_HEADER;
+        else if (v > 0xFFFFFFFFull) st = CJ_ST_TOO_BIG;
+        else *out = (size_t)v;
+        break;
+    }
+    case CJ_SNAPPY_FRAMED: {
+        uint64_t tot = 0;
+        st = cj::snappy_frame_walk(s, n, nullptr, &tot);
+        *out = (size_t)tot;
+        break;
+    }
+    case CJ_LZ4_BLOCK:
+        *out = n * 255;  // LZ4's maximum expansion; callers normally know the size (prefix / output_len)
+        exact = false;
+        break;
+    case CJ_LZ4_FRAME: st = lz4f_bound_host(s, n, out, &exact); break;
+    case CJ_ZSTD: st = cj_zstd_bound_host(s, n, out, &exact); break;
+    default: return CJ_E_INVALID_ARG;
+    }
+    if (st != CJ_OK) {
+        cj_set_error("%s", cj_status_string(st));
+        return CJ_E_UNIT_FAILED;
+    }
+    if (want_exact && !exact) {
+        cj_set_error("the stream does not record its decompressed size");
+        return CJ_E_UNIT_FAILED;
+    }
+    return CJ_OK;
+}
+
+extern "C" int cj_decompressed_len(cj_codec codec, const void* src, size_t n, size_t* out) { return decompressed_bound(codec, src, n, out, true); }
+extern "C" int cj_decompress_bound(cj_codec codec, const void* src, size_t n, size_t* out) { return decompressed_bound(codec, src, n, out, false); }

@@ -1,0 +1,111 @@
+// internal.h — definitions shared by the host-side translation units of libcramjam_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+void cj_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            cj_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
+                         cudaGetErrorString(_e));                                                   \
+            return CJ_E_CUDA;                                                                       \
+        }                                                                                           \
+    } while (0)
+
+namespace cj {
+cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
+cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream);
+cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
+cudaError_t launch_copy_units(uint32_t n, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* len, uint8_t* dst_base,
+                              const uint64_t* dst_off, int sm_count, cudaStream_t stream);
+cudaError_t launch_synth(uint8_t* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, cudaStream_t stream);
+int frames_decompress(cj_ctx* ctx, int codec, int where, const cj_batch* batch);
+int frames_compress(cj_ctx* ctx, int codec, int where, const cj_batch* batch, const cj_params* params);
+}  // namespace cj
+
+// Growable device / pinned scratch buffer.
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CJ_OK;
+        release();
+        size_t want = std::max(bytes + bytes / 8, (size_t)1 << 20);
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            cj_set_error("%s of %zu bytes failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc", want, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return CJ_E_NOMEM;
+        }
+        cap = want;
+        return CJ_OK;
+    }
+    void release() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct cj_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    unsigned* counters = nullptr;  // device work-queue counters
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    uint64_t launches = 0;
+    std::mutex mu;
+    Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
+    Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)
+    cj_ctx() {
+        h_src.pinned = h_dst.pinned = h_desc.pinned = true;
+        f_hsrc.pinned = f_hdst.pinned = f_hdesc.pinned = true;
+    }
+    void release_all() {
+        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc};
+        for (Scratch* s : all) s->release();
+    }
+};
+
+// api.cu: run a block-codec batch whose descriptors and payload already live on the device (caller holds ctx->mu).
+int cj_run_device_batch(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params);
+
+static inline size_t cj_align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Parallel loop over units on host threads (gather into / scatter out of pinned staging).
+template <class F>
+static void cj_parallel_units(size_t n, size_t bytes, F&& f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = bytes < ((size_t)8 << 20) ? 1 : std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, n});
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=, &f]() {
+            for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; i++) f(i);
+        });
+    for (auto& t : th) t.join();
+}

@@ -1,8 +1,6 @@
 // stubs.cu — entry points whose kernels are not built yet.  They fail loudly (no CPU fallback).
-#include "common.cuh"
-void cj_set_error(const char* fmt, ...);
+#include "internal.h"
 namespace cj {
-int frames_decompress(cj_ctx*, int codec, int, const cj_batch*) { cj_set_error("codec %d decode not built yet", codec); return CJ_E_INVALID_ARG; }
-int frames_compress(cj_ctx*, int codec, int, const cj_batch*, const cj_params*) { cj_set_error("codec %d encode not built yet", codec); return CJ_E_INVALID_ARG; }
+int zstd_decompress_host(cj_ctx*, int, const cj_batch*) { cj_set_error("zstd decode is not built yet"); return CJ_E_INVALID_ARG; }
 }
-extern "C" int cj_decompressed_len(cj_codec, const void*, size_t, size_t*) { return CJ_E_INVALID_ARG; }
+int cj_zstd_bound_host(const uint8_t*, size_t, size_t*, bool*) { return CJ_ST_UNSUPPORTED; }

@@ -120,6 +120,9 @@ int cj_ctx_last_kernel_ms(cj_ctx* ctx, float* ms);
 /* ---- size helpers (pure host arithmetic / header parsing on HOST memory) ------------------- */
 size_t cj_compress_bound(cj_codec codec, size_t src_len);
 int cj_decompressed_len(cj_codec codec, const void* src, size_t src_len, size_t* out);
+/* Upper bound of the decompressed size from headers alone (exact whenever the format records it):
+ * what a host uses to size the output Vec when the caller gave no output_len. */
+int cj_decompress_bound(cj_codec codec, const void* src, size_t src_len, size_t* out);
 
 /* ---- batched core -------------------------------------------------------------------------- */
 int cj_decompress_batch(cj_ctx* ctx, cj_codec codec, cj_mem where, const cj_batch* batch);
