@@ -137,6 +137,11 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, c->counters, c->sm_count, c->stream);
         else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, c->counters, c->sm_count, c->stream);
+        else if (codec == CJ_ZSTD) {
+            int rc = c->z_lit.ensure(cj::zstd_scratch_bytes(c->sm_count, b.n));
+            if (rc) return rc;
+            e = cj::launch_zstd_decode(b, c->counters, (uint8_t*)c->z_lit.p, c->sm_count, c->stream);
+        }
         else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
     } else {
         int accel = params && params->acceleration > 0 ? params->acceleration : 1;
@@ -268,10 +273,10 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     }
     std::lock_guard<std::mutex> g(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
-    if (codec == CJ_SNAPPY_FRAMED || codec == CJ_ZSTD || (codec == CJ_LZ4_FRAME && compress))
+    if (codec == CJ_SNAPPY_FRAMED || ((codec == CJ_LZ4_FRAME || codec == CJ_ZSTD) && compress))
         return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
     // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
-    if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
+    if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME && codec != CJ_ZSTD) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
     if (where == CJ_DEVICE) {
         if (bt->n > 0xffffffffull) { cj_set_error("too many units"); return CJ_E_INVALID_ARG; }
         cj::Batch b;

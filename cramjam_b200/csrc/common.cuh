@@ -25,6 +25,10 @@ struct Batch {
 
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) { return __ldg(p); }
 
+__device__ __forceinline__ uint32_t rd32g(const uint8_t* p) {  // unaligned little-endian u32 from read-only input
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+}
+
 // Next unit index from the grid-wide work queue (one atomic per warp).
 __device__ __forceinline__ uint32_t next_unit(unsigned* counter, int lane) {
     uint32_t v = 0;

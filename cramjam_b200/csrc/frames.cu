@@ -131,10 +131,6 @@ __global__ void __launch_bounds__(128) crc32c_units_kernel(uint32_t n, const uin
 // ================================================================================================
 // LZ4 frame decode: one warp per frame stream (concatenated + skippable frames included)
 // ================================================================================================
-__device__ __forceinline__ uint32_t rd32g(const uint8_t* p) {
-    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
-}
-
 __device__ int32_t lz4f_decode_stream(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint32_t cap, uint8_t* smem_warp, int lane,
                                       uint32_t* produced) {
     OutRing out;
@@ -727,8 +723,6 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
 
 }  // namespace
 
-int zstd_decompress_host(cj_ctx* c, int where, const cj_batch* bt);  // zstd_decode.cu
-
 int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
     if (where == CJ_DEVICE) {
         cj_set_error("frame containers (codec %d) take host-visible input: pass CJ_HOST or CJ_PINNED", codec);
@@ -736,7 +730,6 @@ int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
     }
     if (bt->n == 0) return CJ_OK;
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_decompress(c, where, bt);
-    if (codec == CJ_ZSTD) return zstd_decompress_host(c, where, bt);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }

@@ -149,6 +149,19 @@ struct OutRing {
         __syncwarp();
     }
 
+    // Same, for a source this kernel itself wrote earlier (zstd literal buffer): L2-coherent loads.
+    __device__ __forceinline__ void put_literals_coherent(const uint8_t* s, uint32_t len) {
+        while (len) {
+            uint32_t c = min(len, CHUNK);
+            make_room();
+            for (uint32_t i = lane; i < c; i += 32) sts8(ridx(op + i), __ldcg(s + i));
+            op += c;
+            s += c;
+            len -= c;
+        }
+        __syncwarp();
+    }
+
     // Serial path: back-reference copy; caller guarantees 1 <= off <= op.
     __device__ __forceinline__ void put_match(uint32_t off, uint32_t len) {
         if (len <= 32 && off + 32 <= (uint32_t)ORING && op - flushed < FLUSH_T) {

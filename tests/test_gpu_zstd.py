@@ -1,0 +1,83 @@
+"""-m gpu tests: Zstandard frame decode kernel vs the CPU oracle / libzstd, through the C ABI."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import corpus
+import oracle as O
+import syslibs as S
+from cramjam_b200 import _capi as capi
+from gpu_util import assert_same_as_oracle, ctx
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PLAINTEXT = open(os.path.join(G, "plaintext.txt"), "rb").read()
+CASES = corpus.edge_cases()
+
+
+def test_golden_fixture():
+    # reference tests/test_integration.py:32-50, row zstd/zst
+    f = open(os.path.join(G, "plaintext.txt.zst"), "rb").read()
+    outs, st = ctx().run_host_units(capi.ZSTD, False, [f], [len(PLAINTEXT)])
+    assert st[0] == 0 and outs[0] == PLAINTEXT
+    out = C.c_size_t()
+    assert capi.lib().cj_decompressed_len(capi.ZSTD, f, len(f), C.byref(out)) == 0 and out.value == 857
+
+
+def test_sknow_is_an_error():
+    outs, st = ctx().run_host_units(capi.ZSTD, False, [b"sknow"], [100])
+    assert st[0] != 0
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+@pytest.mark.parametrize("kw", [dict(level=1), dict(level=3), dict(level=3, checksum=True), dict(level=9), dict(level=19),
+                                dict(level=3, window_log=17), dict(level=-5), dict(level=3, content_size=False)])
+def test_libzstd_frames_decode_bit_exact(kw):
+    units = [S.zstd_compress(d, **kw) for d in CASES]
+    outs, st = ctx().run_host_units(capi.ZSTD, False, units, [len(d) for d in CASES])
+    assert (st == 0).all(), [(i, int(s)) for i, s in enumerate(st) if s]
+    assert outs == CASES
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+def test_concatenated_and_skippable_frames_and_capacity():
+    a, b = S.zstd_compress(b"one " * 1000), S.zstd_compress(corpus.text(5000, 9), checksum=True)
+    skip = (0x184D2A50).to_bytes(4, "little") + (3).to_bytes(4, "little") + b"abc"
+    want = b"one " * 1000 + corpus.text(5000, 9)
+    outs, st = ctx().run_host_units(capi.ZSTD, False, [a + skip + b, a + skip + b, b""], [len(want), len(want) - 1, 0])
+    assert st[0] == 0 and outs[0] == want
+    assert st[1] == 5                                      # DST_SMALL
+    assert st[2] == 0 and outs[2] == b""                   # empty input decodes to nothing (streaming decoder semantics)
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+def test_hostile_frames_match_oracle():
+    rng = np.random.default_rng(11)
+    units, caps = [], []
+    for d, kw in ((corpus.lz_model(20000, 3), dict(level=3, checksum=True)), (corpus.text(30000, 4), dict(level=1)), (b"q" * 5000, dict(level=3))):
+        f = S.zstd_compress(d, **kw)
+        for _ in range(250):
+            m = bytearray(f)
+            k = int(rng.integers(0, 3))
+            if k == 0:
+                m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            elif k == 1:
+                m = m[: int(rng.integers(0, len(m)))]
+            else:
+                m[int(rng.integers(0, len(m)))] = int(rng.integers(0, 256))
+            units.append(bytes(m))
+            caps.append(len(d))
+    assert_same_as_oracle(capi.ZSTD, units, caps, "host")
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+def test_synthetic_256k_frames_level3():
+    """BASELINE configs[3] shape at a size the oracle finishes in seconds: 128 x 256 KiB level-3 frames."""
+    n, U = 128, 262144
+    data = capi.synth_host(n * 4, 65536, seed=0xC0FFEE)
+    blocks = [data[i * U:(i + 1) * U].tobytes() for i in range(n)]
+    units = [S.zstd_compress(b, 3) for b in blocks]
+    outs, st = ctx().run_host_units(capi.ZSTD, False, units, [U] * n)
+    assert (st == 0).all() and outs == blocks
