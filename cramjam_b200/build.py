@@ -36,6 +36,35 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST_SRC = os.path.join(HERE, "host", "cramjam_module.cpp")
+
+
+def host_module_path():
+    import sysconfig
+    return os.path.join(HERE, "cramjam" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_host(force=False):
+    """Builds the C++ (pybind11) host binding cramjam_b200/cramjam.*.so against libcramjam_cuda.so."""
+    import sysconfig
+    import pybind11
+    out = host_module_path()
+    deps = [HOST_SRC, os.path.join(HERE, "..", "include", "cramjam_cuda.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    build()
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-Wall",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], HOST_SRC, "-o", out,
+           "-L", HERE, "-lcramjam_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building the cramjam host module")
+    return out
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_host(force=True)
     print(OUT)
+    print(host_module_path())

@@ -123,6 +123,7 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
         return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16;
     }
     case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8;
+    case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18;  // >= ZSTD_compressBound for the raw-block frames this build emits
     default: return 0;
     }
 }
