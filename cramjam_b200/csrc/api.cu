@@ -83,6 +83,12 @@ void cj_ctx_destroy(cj_ctx* c) {
     if (c->counters) cudaFree(c->counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    for (int i = 0; i < cj_ctx::PIPE; i++) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -131,22 +137,23 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
 }  // extern "C"
 
 // ---- kernel dispatch on a device-resident batch ------------------------------------------------
-static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params) {
+static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params, int slot = 0) {
     if (b.n == 0) return CJ_OK;
     cudaError_t e;
+    unsigned* counters = c->counters + (slot & 63);
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, c->counters, c->sm_count, c->stream);
-        else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, c->counters, c->sm_count, c->stream);
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream);
+        else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, counters, c->sm_count, c->stream);
         else if (codec == CJ_ZSTD) {
             int rc = c->z_lit.ensure(cj::zstd_scratch_bytes(c->sm_count, b.n));
             if (rc) return rc;
-            e = cj::launch_zstd_decode(b, c->counters, (uint8_t*)c->z_lit.p, c->sm_count, c->stream);
+            e = cj::launch_zstd_decode(b, counters, (uint8_t*)c->z_lit.p, c->sm_count, c->stream);
         }
         else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
     } else {
         int accel = params && params->acceleration > 0 ? params->acceleration : 1;
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, c->counters, c->sm_count, accel, c->stream);
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, accel, c->stream);
         else { cj_set_error("codec %d has no device-resident batch encoder", codec); return CJ_E_INVALID_ARG; }
     }
     cudaEventRecord(c->ev1, c->stream);
@@ -156,6 +163,83 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         cj_set_error("kernel launch failed: %s", cudaGetErrorString(e));
         return CJ_E_CUDA;
     }
+    return CJ_OK;
+}
+
+// Dense pinned arenas, units in ascending order on both sides: split the batch into chunks and run
+// H2D(c+1) | kernel(c) | D2H(c-1) on three streams so PCIe moves in both directions while the SMs decode.
+// A chunk's payload is written straight into the caller's memory only if every unit of the chunk filled
+// its slot exactly; any other chunk takes the per-unit path so no byte past dst_len[i] is touched.
+static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_batch* bt, const cj_params* params, uint64_t s_lo, uint64_t s_hi,
+                                uint64_t d_lo, uint64_t d_hi) {
+    const size_t n = bt->n;
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    uint8_t* hd = (uint8_t*)bt->dst_base;
+    const size_t s_bytes = (size_t)(s_hi - s_lo), d_bytes = (size_t)(d_hi - d_lo);
+    int rc;
+    if ((rc = c->d_src.ensure(s_bytes + 16))) return rc;
+    if ((rc = c->d_dst.ensure(d_bytes + 16))) return rc;
+    const size_t desc_bytes = n * (5 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    if ((rc = c->d_desc.ensure(desc_bytes))) return rc;
+    if ((rc = c->h_desc.ensure(desc_bytes))) return rc;
+    if (!c->s_h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < cj_ctx::PIPE; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    uint64_t* hq = (uint64_t*)c->h_desc.p;
+    for (size_t i = 0; i < n; i++) {
+        hq[i] = bt->src_off[i] - s_lo;
+        hq[2 * n + i] = bt->dst_off[i] - d_lo;
+    }
+    memcpy(hq + n, bt->src_len, n * 8);
+    memcpy(hq + 3 * n, bt->dst_cap, n * 8);
+    uint64_t* dq = (uint64_t*)c->d_desc.p;
+    CUDA_TRY(cudaMemcpyAsync(dq, hq, n * 32, cudaMemcpyHostToDevice, c->stream));
+    const int chunks = cj_ctx::PIPE;
+    size_t first[cj_ctx::PIPE + 1];
+    for (int k = 0; k <= chunks; k++) first[k] = n * (size_t)k / chunks;
+    // enqueue all input copies and kernels
+    for (int k = 0; k < chunks; k++) {
+        const size_t a = first[k], b = first[k + 1];
+        if (a == b) continue;
+        const uint64_t lo = bt->src_off[a] - s_lo, hi = bt->src_off[b - 1] + bt->src_len[b - 1] - s_lo;
+        CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->d_src.p + lo, hs + s_lo + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->s_h2d));
+        CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        cj::Batch bb;
+        bb.n = (uint32_t)(b - a);
+        bb.src_base = (const uint8_t*)c->d_src.p; bb.src_off = dq + a; bb.src_len = dq + n + a;
+        bb.dst_base = (uint8_t*)c->d_dst.p; bb.dst_off = dq + 2 * n + a; bb.dst_cap = dq + 3 * n + a;
+        bb.dst_len = dq + 4 * n + a; bb.status = (int32_t*)(dq + 5 * n) + a;
+        if ((rc = run_device(c, codec, compress, bb, params, k))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hq + 4 * n + a, dq + 4 * n + a, (b - a) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)(hq + 5 * n) + a, (int32_t*)(dq + 5 * n) + a, (b - a) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
+    }
+    // drain: as each chunk's kernel finishes, send its output home
+    const uint64_t* dl = hq + 4 * n;
+    for (int k = 0; k < chunks; k++) {
+        const size_t a = first[k], b = first[k + 1];
+        if (a == b) continue;
+        CUDA_TRY(cudaEventSynchronize(c->ev_k[k]));
+        bool tight = true;
+        for (size_t i = a; i < b && tight; i++) tight = dl[i] == bt->dst_cap[i];
+        if (tight) {
+            const uint64_t lo = bt->dst_off[a] - d_lo, hi = bt->dst_off[b - 1] + bt->dst_cap[b - 1] - d_lo;
+            CUDA_TRY(cudaMemcpyAsync(hd + d_lo + lo, (uint8_t*)c->d_dst.p + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->s_d2h));
+        } else {
+            for (size_t i = a; i < b; i++)
+                if (dl[i]) CUDA_TRY(cudaMemcpyAsync(hd + bt->dst_off[i], (uint8_t*)c->d_dst.p + (bt->dst_off[i] - d_lo), (size_t)dl[i], cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(bt->dst_len, hq + 4 * n, n * 8);
+    memcpy(bt->status, hq + 5 * n, n * 4);
     return CJ_OK;
 }
 
@@ -177,6 +261,12 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
     const bool direct = where == CJ_PINNED;
     const bool s_span = direct && (s_hi - s_lo) <= s_sum + s_sum / 4 + 64 * n;
     const bool d_span = direct && (d_hi - d_lo) <= d_sum + 16 * n;
+    if (s_span && d_span && n >= 256 && s_sum + d_sum >= ((uint64_t)64 << 20) && (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK)) {
+        bool ascending = true;
+        for (size_t i = 1; i < n && ascending; i++)
+            ascending = bt->src_off[i] >= bt->src_off[i - 1] + bt->src_len[i - 1] && bt->dst_off[i] >= bt->dst_off[i - 1] + bt->dst_cap[i - 1];
+        if (ascending) return run_pinned_pipelined(c, codec, compress, bt, params, s_lo, s_hi, d_lo, d_hi);
+    }
 
     // device-side layout
     std::vector<uint64_t> so(n), doff(n);

@@ -76,6 +76,9 @@ struct cj_ctx {
     unsigned* counters = nullptr;  // device work-queue counters
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    static constexpr int PIPE = 8;                 // chunks of the pinned-arena pipeline (api.cu)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
+    cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
     std::mutex mu;
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)

@@ -150,3 +150,27 @@ def test_pinned_path_matches_host_path():
     # CJ_PINNED with ordinary numpy memory is still legal for cudaMemcpyAsync (it just is not DMA-direct)
     b, _ = gpu_decode_host(capi.LZ4_BLOCK, units, [U] * n, where=capi.PINNED)
     assert a == b == [data[i * U:(i + 1) * U].tobytes() for i in range(n)]
+
+
+@pytest.mark.parametrize("codec", [capi.LZ4_BLOCK, capi.SNAPPY_RAW])
+def test_pinned_pipelined_path(codec):
+    """Dense arenas >= 64 MiB through CJ_PINNED take the chunked H2D | kernel | D2H pipeline; one chunk holds a
+    corrupt unit and must fall back to per-unit copies without disturbing its neighbours."""
+    n, U = 1536, 65536
+    data = capi.synth_host(n, U, seed=77)
+    comp = O.lz4_block_compress if codec == capi.LZ4_BLOCK else O.snappy_raw_compress
+    units = [comp(data[i * U:(i + 1) * U].tobytes()) for i in range(n)]
+    bad = 700
+    units[bad] = units[bad][:100]                      # truncated stream -> error status
+    src, so, sl = arena(units)
+    do = np.arange(n, dtype=np.uint64) * U
+    dc = np.full(n, U, dtype=np.uint64)
+    dst = np.full(n * U, 0xAB, dtype=np.uint8)
+    dl = np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=np.int32)
+    ctx().decompress_batch(codec, capi.PINNED, n, src, so, sl, dst, do, dc, dl, st)
+    assert st[bad] != 0 and (np.delete(st, bad) == 0).all()
+    assert (dst[bad * U:(bad + 1) * U] == 0xAB).all()   # nothing written for the failed unit
+    ok = np.ones(n * U, dtype=bool)
+    ok[bad * U:(bad + 1) * U] = False
+    assert np.array_equal(dst[ok], data[ok])
