@@ -85,6 +85,7 @@ struct OutRing {
     static_assert(ORING >= 2 * TMAX + FLUSH_T + CHUNK + 32, "far sources of a batch must already be drained");
 
     uint32_t ring;     // shared-space address of this warp's output ring
+    const uint8_t* ring_g;  // the same ring as a generic pointer (lane-parallel copies mix ring and global sources)
     uint8_t* dst;
     uint32_t a;        // dst misalignment (dst & 15); ring index = (pos + a) & OMASK
     uint32_t op;       // bytes produced so far
@@ -94,6 +95,7 @@ struct OutRing {
 
     __device__ __forceinline__ void init(uint8_t* ring_, uint8_t* dst_, int lane_) {
         ring = smem_addr(ring_);
+        ring_g = ring_;
         dst = dst_;
         a = (uint32_t)((uintptr_t)dst_ & 15u);
         op = 0;
@@ -291,6 +293,7 @@ __device__ __forceinline__ int snappy_serial_step(const uint8_t* __restrict__ sr
 // ------------------------------------------------------------------------------------------------
 struct InRing {
     uint32_t ring;  // shared-space address of this warp's input ring
+    const uint8_t* ring_g;  // generic pointer to the same ring
     const uint8_t* src;
     uint32_t n;
     uint32_t a;       // src misalignment; "g" coordinate = pos + a, ring index = g & IMASK
@@ -299,6 +302,7 @@ struct InRing {
 
     __device__ __forceinline__ void init(uint8_t* ring_, const uint8_t* src_, uint32_t n_, int lane_) {
         ring = smem_addr(ring_);
+        ring_g = ring_;
         src = src_;
         n = n_;
         a = (uint32_t)((uintptr_t)src_ & 15u);
@@ -399,23 +403,9 @@ __device__ __forceinline__ void parse_window(const InRing& in, uint32_t& pp, uin
 }
 
 // Lane-parallel copy of up to 16 bytes per lane (nl = 0 for lanes that sit out); src/dst must not overlap.
-__device__ __forceinline__ void lane_copy16(uint32_t sp, uint32_t dp, uint32_t nl) {
-    const uint32_t mx = __reduce_max_sync(FULL, nl);
-    for (uint32_t b = 0; b < mx; b += 4) {
-        uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        if (b < nl) v0 = lds8(sp + b);
-        if (b + 1 < nl) v1 = lds8(sp + b + 1);
-        if (b + 2 < nl) v2 = lds8(sp + b + 2);
-        if (b + 3 < nl) v3 = lds8(sp + b + 3);
-        if (b < nl) sts8(dp + b, v0);
-        if (b + 1 < nl) sts8(dp + b + 1, v1);
-        if (b + 2 < nl) sts8(dp + b + 2, v2);
-        if (b + 3 < nl) sts8(dp + b + 3, v3);
-    }
-}
-
-// Same, source in global memory (drained output re-read through L1/L2; plain coherent loads).
-__device__ __forceinline__ void lane_copy16_global(const uint8_t* gp, uint32_t dp, uint32_t nl) {
+// The source is a GENERIC pointer: the input ring or the output ring in shared memory, or drained output
+// in global memory (re-read through L1/L2 with plain coherent loads) — one instruction stream serves all.
+__device__ __forceinline__ void lane_copy16(const uint8_t* gp, uint32_t dp, uint32_t nl) {
     const uint32_t mx = __reduce_max_sync(FULL, nl);
     for (uint32_t b = 0; b < mx; b += 4) {
         uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
@@ -492,24 +482,20 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
     const uint32_t ldi = (o + out.a) & OMASK, lsi = (lsrc + in.a) & IMASK;
     const uint32_t mdi = (m + out.a) & OMASK, msi = (m - off + out.a) & OMASK;
     const bool shortL = LL != 0 && LL <= 16 && ldi + LL <= (uint32_t)ORING && lsi + LL <= (uint32_t)IRING;
-    const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING;  // lane-parallel candidates
-    const bool nearM = smallM && off <= FAR_T && msi + ML <= (uint32_t)ORING;              // source in the ring
-    const bool farM = smallM && off > FAR_T;                                               // source re-read from global (L1/L2)
+    const bool far = off > FAR_T;                                                              // source re-read from global (L1/L2)
+    const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING && (far || msi + ML <= (uint32_t)ORING);
+    const uint8_t* msrc = far ? out.dst + (m - off) : out.ring_g + msi;                          // lane-parallel match source
     bool pending = ML != 0;
 
     // ---- pass 1: literals (always ready); for snappy also every copy whose source precedes the batch ----
     {
-        uint32_t sp = in.ring + lsi, dp = out.ring + ldi, nl = shortL ? LL : 0u;
-        bool early = false;
+        const uint8_t* sp = in.ring_g + lsi;
+        uint32_t dp = out.ring + ldi, nl = shortL ? LL : 0u;
         if (CODEC == CJ_SNAPPY_RAW) {
-            early = pending && se <= O;
-            if (early && nearM) { sp = out.ring + msi; dp = out.ring + mdi; nl = ML; }
+            const bool early = pending && smallM && se <= O;
+            if (early) { sp = msrc; dp = out.ring + mdi; nl = ML; pending = false; }
         }
         lane_copy16(sp, dp, nl);
-        if (CODEC == CJ_SNAPPY_RAW) {
-            lane_copy16_global(out.dst + (m - off), out.ring + mdi, (early && farM) ? ML : 0u);
-            if (early && (nearM || farM)) pending = false;
-        }
         uint32_t lm = __ballot_sync(FULL, LL != 0 && !shortL);
         while (lm) {
             const int j = __ffs(lm) - 1;
@@ -526,9 +512,8 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
         while (pm) {
             const uint32_t F = __shfl_sync(FULL, m, __ffs(pm) - 1);  // all output below F is complete
             const bool ready = pending && se <= F;
-            lane_copy16(out.ring + msi, out.ring + mdi, (ready && nearM) ? ML : 0u);
-            lane_copy16_global(out.dst + (m - off), out.ring + mdi, (ready && farM) ? ML : 0u);
-            uint32_t lm = __ballot_sync(FULL, ready && !nearM && !farM);
+            lane_copy16(msrc, out.ring + mdi, (ready && smallM) ? ML : 0u);
+            uint32_t lm = __ballot_sync(FULL, ready && !smallM);
             while (lm) {  // long, self-overlapping or ring-wrapping copies: the whole warp moves one at a time
                 const int j = __ffs(lm) - 1;
                 lm &= lm - 1;
