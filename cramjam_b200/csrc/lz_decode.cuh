@@ -420,8 +420,102 @@ __device__ __forceinline__ void lane_copy16(const uint8_t* gp, uint32_t dp, uint
     }
 }
 
-// Executes the first cnt (<= 32) queued elements, one lane each.  Returns how many were executed
-// (a prefix); 0 means the first element must go through the serial path.
+// How exec_lanes bounds the output: RULE_LEN  = no element may pass `limit` (Snappy announced length, zstd capacity);
+//                                    RULE_LZ4  = LZ4_decompress_safe's dstCapacity rules (MFLIMIT 12 / LASTLITERALS 5).
+constexpr int RULE_LEN = 0, RULE_LZ4 = 1;
+
+// Executes up to 32 elements, one lane each.  Lane j (< cnt) holds a literal run of LL bytes whose k-th byte is
+// lbase[(lidx + k) & lmask] (input ring: lmask = IMASK; a linear buffer: lmask = ~0u) followed by a back-reference
+// of ML bytes at distance off (ML == 0: none).  Returns how many elements were executed (a prefix of the lanes);
+// element k (if k < cnt) failed a check or did not fit the batch and must be handled by the caller.
+template <int RULE, bool EARLY_COPIES>
+__device__ __forceinline__ uint32_t exec_lanes(OutRing& out, uint32_t cnt, uint32_t LL, const uint8_t* lbase, uint32_t lidx, uint32_t lmask,
+                                               uint32_t ML, uint32_t off, uint32_t limit, int lane) {
+    if ((uint32_t)lane >= cnt) { LL = 0; ML = 0; }
+    const uint32_t tot = LL + ML;
+    uint32_t incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t O = out.op;
+    const uint32_t o = O + incl - tot;
+    bool bad = false;
+    if ((uint32_t)lane < cnt) {
+        bad = incl > TMAX;
+        if (ML) bad |= off == 0 || off > o + LL - out.base;
+        if (RULE == RULE_LEN) bad |= incl > limit - O;
+        else bad |= (o + LL + 12 > limit) || (o + tot + 5 > limit);
+    }
+    const uint32_t cm = __ballot_sync(FULL, bad);
+    const uint32_t k = cm ? __ffs(cm) - 1 : cnt;
+    if (k == 0) return 0;
+    if ((uint32_t)lane >= k) { LL = 0; ML = 0; }
+    const uint32_t T = __shfl_sync(FULL, incl, k - 1);
+
+    // Per-lane addressing.  m = where the match part lands; se = end of the distinct source bytes it needs.
+    const uint32_t m = o + LL;
+    const uint32_t se = m - off + min(ML, off);
+    const uint32_t ldi = (o + out.a) & OMASK, lsi = lidx & lmask;
+    const uint32_t mdi = (m + out.a) & OMASK, msi = (m - off + out.a) & OMASK;
+    const bool shortL = LL != 0 && LL <= 16 && ldi + LL <= (uint32_t)ORING && (lmask == 0xFFFFFFFFu || lsi + LL <= lmask + 1);
+    const bool far = off > FAR_T;                                                              // source re-read from global (L1/L2)
+    const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING && (far || msi + ML <= (uint32_t)ORING);
+    const uint8_t* msrc = far ? out.dst + (m - off) : out.ring_g + msi;                          // lane-parallel match source
+    bool pending = ML != 0;
+
+    // ---- pass 1: literals (always ready); with EARLY_COPIES also every copy of a literal-free lane whose source precedes the batch ----
+    {
+        const uint8_t* sp = lbase + lsi;
+        uint32_t dp = out.ring + ldi, nl = shortL ? LL : 0u;
+        if (EARLY_COPIES) {
+            const bool early = pending && LL == 0 && smallM && se <= O;
+            if (early) { sp = msrc; dp = out.ring + mdi; nl = ML; pending = false; }
+        }
+        lane_copy16(sp, dp, nl);
+        uint32_t lm = __ballot_sync(FULL, LL != 0 && !shortL);
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t jo = __shfl_sync(FULL, o, j), jl = __shfl_sync(FULL, LL, j), js = __shfl_sync(FULL, lidx, j), jmask = __shfl_sync(FULL, lmask, j);
+            const uint8_t* jb = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL, (unsigned long long)lbase, j));
+            for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jo + i), jb[(js + i) & jmask]);
+        }
+    }
+    __syncwarp();
+
+    // ---- back-references: dependency rounds ----
+    {
+        uint32_t pm = __ballot_sync(FULL, pending);
+        while (pm) {
+            const uint32_t F = __shfl_sync(FULL, m, __ffs(pm) - 1);  // all output below F is complete
+            const bool ready = pending && se <= F;
+            lane_copy16(msrc, out.ring + mdi, (ready && smallM) ? ML : 0u);
+            uint32_t lm = __ballot_sync(FULL, ready && !smallM);
+            while (lm) {  // long, self-overlapping or ring-wrapping copies: the whole warp moves one at a time
+                const int j = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const uint32_t jm = __shfl_sync(FULL, m, j), jl = __shfl_sync(FULL, ML, j), jf = __shfl_sync(FULL, off, j);
+                const uint32_t s = jm - jf;
+                if (jf >= jl) {
+                    if (jf > FAR_T) for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), out.dst[s + i]);
+                    else for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i)));
+                } else {
+                    for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i % jf)));
+                }
+            }
+            pending = pending && !ready;
+            __syncwarp();
+            pm = __ballot_sync(FULL, pending);
+        }
+    }
+    out.op = O + T;
+    return k;
+}
+
+// Executes the first cnt (<= 32) queued LZ4 sequences / Snappy elements, one lane each.  Returns how many were
+// executed (a prefix); 0 means the first element must go through the serial path.
 template <int CODEC>
 __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, uint32_t q, uint32_t cnt, uint32_t limit, int lane) {
     __syncwarp();
@@ -454,85 +548,7 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
             ML = ml + 4;
         }
     }
-    const uint32_t tot = LL + ML;
-    uint32_t incl = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const uint32_t O = out.op;
-    const uint32_t o = O + incl - tot;
-    bool bad = false;
-    if ((uint32_t)lane < cnt) {
-        bad = incl > TMAX;
-        if (ML) bad |= off == 0 || off > o + LL - out.base;
-        if (CODEC == CJ_SNAPPY_RAW) bad |= incl > limit - O;
-        else bad |= (o + LL + 12 > limit) || (o + tot + 5 > limit);
-    }
-    const uint32_t cm = __ballot_sync(FULL, bad);
-    const uint32_t k = cm ? __ffs(cm) - 1 : cnt;
-    if (k == 0) return 0;
-    if ((uint32_t)lane >= k) { LL = 0; ML = 0; }
-    const uint32_t T = __shfl_sync(FULL, incl, k - 1);
-
-    // Per-lane addressing.  m = where the match part lands; se = end of the distinct source bytes it needs.
-    const uint32_t m = o + LL;
-    const uint32_t se = m - off + min(ML, off);
-    const uint32_t ldi = (o + out.a) & OMASK, lsi = (lsrc + in.a) & IMASK;
-    const uint32_t mdi = (m + out.a) & OMASK, msi = (m - off + out.a) & OMASK;
-    const bool shortL = LL != 0 && LL <= 16 && ldi + LL <= (uint32_t)ORING && lsi + LL <= (uint32_t)IRING;
-    const bool far = off > FAR_T;                                                              // source re-read from global (L1/L2)
-    const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING && (far || msi + ML <= (uint32_t)ORING);
-    const uint8_t* msrc = far ? out.dst + (m - off) : out.ring_g + msi;                          // lane-parallel match source
-    bool pending = ML != 0;
-
-    // ---- pass 1: literals (always ready); for snappy also every copy whose source precedes the batch ----
-    {
-        const uint8_t* sp = in.ring_g + lsi;
-        uint32_t dp = out.ring + ldi, nl = shortL ? LL : 0u;
-        if (CODEC == CJ_SNAPPY_RAW) {
-            const bool early = pending && smallM && se <= O;
-            if (early) { sp = msrc; dp = out.ring + mdi; nl = ML; pending = false; }
-        }
-        lane_copy16(sp, dp, nl);
-        uint32_t lm = __ballot_sync(FULL, LL != 0 && !shortL);
-        while (lm) {
-            const int j = __ffs(lm) - 1;
-            lm &= lm - 1;
-            const uint32_t jo = __shfl_sync(FULL, o, j), jl = __shfl_sync(FULL, LL, j), js = __shfl_sync(FULL, lsrc, j);
-            for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jo + i), in.byte(js + i));
-        }
-    }
-    __syncwarp();
-
-    // ---- back-references: dependency rounds ----
-    {
-        uint32_t pm = __ballot_sync(FULL, pending);
-        while (pm) {
-            const uint32_t F = __shfl_sync(FULL, m, __ffs(pm) - 1);  // all output below F is complete
-            const bool ready = pending && se <= F;
-            lane_copy16(msrc, out.ring + mdi, (ready && smallM) ? ML : 0u);
-            uint32_t lm = __ballot_sync(FULL, ready && !smallM);
-            while (lm) {  // long, self-overlapping or ring-wrapping copies: the whole warp moves one at a time
-                const int j = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const uint32_t jm = __shfl_sync(FULL, m, j), jl = __shfl_sync(FULL, ML, j), jf = __shfl_sync(FULL, off, j);
-                const uint32_t s = jm - jf;
-                if (jf >= jl) {
-                    if (jf > FAR_T) for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), out.dst[s + i]);
-                    else for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i)));
-                } else {
-                    for (uint32_t i = lane; i < jl; i += 32) sts8(out.ridx(jm + i), lds8(out.ridx(s + i % jf)));
-                }
-            }
-            pending = pending && !ready;
-            __syncwarp();
-            pm = __ballot_sync(FULL, pending);
-        }
-    }
-    out.op = O + T;
-    return k;
+    return exec_lanes<CODEC == CJ_SNAPPY_RAW ? RULE_LEN : RULE_LZ4, CODEC == CJ_SNAPPY_RAW>(out, cnt, LL, in.ring_g, lsrc + in.a, IMASK, ML, off, limit, lane);
 }
 
 // Decodes one compressed stream (an LZ4 block, or the element stream of a Snappy raw block after its

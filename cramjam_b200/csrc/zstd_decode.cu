@@ -55,46 +55,49 @@ struct FwdBits {
     }
 };
 
+// Backward bit reader.  A 64-bit window of the stream is kept in registers (two aligned 8-byte loads + a funnel
+// shift per refill, every ~40-56 consumed bits); a read is a shift and a mask.  The aligned loads may touch up to
+// 15 bytes around the stream but never leave the 16-byte-padded source unit; those bits are never used.
 struct BackBits {
     const uint8_t* p;
-    uint32_t n;
-    int32_t pos;      // bits still unread (may go negative = over-read)
-    uint64_t win;     // cached bytes [wbyte, wbyte + 8)
-    int32_t wbyte;
+    int32_t pos;   // bits still unread (may go negative = over-read)
+    int32_t wbit;  // stream bit index of win's bit 0 (multiple of 8)
+    uint64_t win;
     __device__ __forceinline__ bool init(const uint8_t* p_, uint32_t n_) {
         p = p_;
-        n = n_;
-        wbyte = -1000;
         win = 0;
+        pos = 0;
+        wbit = 0;
         if (n_ == 0) return false;
         const uint32_t last = __ldg(p_ + n_ - 1);
         if (last == 0) return false;
         pos = (int32_t)(n_ - 1) * 8 + hibit(last);
+        wbit = pos;  // forces a refill on the first read
         return true;
     }
-    __device__ __forceinline__ void load_window(int32_t byte0) {
-        uint64_t w = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int32_t b = byte0 + i;
-            const uint64_t x = (b >= 0 && (uint32_t)b < n) ? __ldg(p + b) : 0;
-            w |= x << (8 * i);
-        }
-        win = w;
-        wbyte = byte0;
+    __device__ __forceinline__ void refill() {  // window = the 8 bytes ending at the byte that holds bit pos-1
+        int32_t wb = ((pos - 1) >> 3) - 7;
+        if (wb < 0) wb = 0;
+        const uint8_t* a = p + wb;
+        const uint64_t* a8 = reinterpret_cast<const uint64_t*>((uintptr_t)a & ~(uintptr_t)7);
+        const uint32_t sh = (uint32_t)((uintptr_t)a & 7) * 8;
+        const uint64_t lo = __ldg(a8), hi = __ldg(a8 + 1);
+        win = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        wbit = wb * 8;
     }
     // bits [pos-nb, pos) as an integer (most significant = highest position), zero-filled below bit 0; nb <= 32
     __device__ __forceinline__ uint32_t peek(int nb) {
-        if (nb == 0) return 0;
-        const int32_t lo = pos - nb;  // may be negative
-        const int32_t lo_c = lo < 0 ? 0 : lo;
-        const int32_t byte0 = lo_c >> 3;
-        if (byte0 < wbyte || (pos > 0 ? (pos - 1) >> 3 : 0) >= wbyte + 8) load_window(byte0 >= 3 ? byte0 - 3 : 0);
-        if (pos <= 0) return 0;
-        const uint32_t have = (uint32_t)(pos - lo_c);  // bits available above bit 0
-        uint64_t v = win >> (lo_c - wbyte * 8);
-        v &= (have >= 64 ? ~0ull : ((1ull << have) - 1));
-        return (uint32_t)(lo < 0 ? v << (uint32_t)(-lo) : v);
+        const int32_t lo = pos - nb;
+        if (lo < wbit) {
+            if (lo < 0) {  // reading past the beginning: zero-fill the missing low bits
+                if (pos <= 0) return 0;
+                if (wbit != 0) refill();
+                const uint64_t v = win & ((1ull << pos) - 1);
+                return (uint32_t)(v << (uint32_t)(-lo));
+            }
+            refill();
+        }
+        return (uint32_t)((win >> (uint32_t)(lo - wbit)) & ((1ull << nb) - 1));
     }
     __device__ __forceinline__ uint32_t read(int nb) {
         const uint32_t v = peek(nb);
@@ -411,45 +414,72 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
         if (!b.init(p, n)) return CJ_ST_CORRUPT;
         uint32_t sl = b.read(z.ll.al), so = b.read(z.of.al), sm = b.read(z.ml.al);
         if (b.pos < 0) return CJ_ST_CORRUPT;
-        for (uint32_t i = 0; i < nseq; i++) {
-            const uint32_t el = z.ll.t[sl], eo = z.of.t[so], em = z.ml.t[sm];
-            const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
-            if (oc > 31 || lc > 35 || mc > 52) return CJ_ST_CORRUPT;
-            const uint64_t ov = (1ull << oc) + b.read((int)oc);
-            const uint32_t mlen = ZS_ML_BASE[mc] + b.read(ZS_ML_BITS[mc]);
-            const uint32_t llen = ZS_LL_BASE[lc] + b.read(ZS_LL_BITS[lc]);
-            if (b.pos < 0) return CJ_ST_CORRUPT;
-            uint32_t off;
-            if (ov > 3) {
-                if (ov - 3 > 0xFFFFFFFFull) return CJ_ST_CORRUPT;
-                off = (uint32_t)(ov - 3);
-                z.rep2 = z.rep1; z.rep1 = z.rep0; z.rep0 = off;
-            } else {
-                const uint32_t idx = (uint32_t)ov - 1 + (llen == 0 ? 1 : 0);
-                if (idx == 0) {
-                    off = z.rep0;
+        for (uint32_t i0 = 0; i0 < nseq; i0 += 32) {
+            // ---- strictly serial part: up to 32 sequences decoded warp-uniformly; lane k keeps the k-th ----
+            uint32_t cnt = min(32u, nseq - i0);
+            int32_t derr = CJ_OK;  // a decode error stops the batch; the sequences before it still run first (their errors come first)
+            uint32_t LL = 0, ML = 0, OFF = 0, LP = 0;
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t el = z.ll.t[sl], eo = z.of.t[so], em = z.ml.t[sm];
+                const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
+                if (oc > 31 || lc > 35 || mc > 52) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                const uint32_t ovx = b.read((int)oc);                        // offset extra bits (<= 31)
+                const uint32_t mlb = ZS_ML_BITS[mc], llb = ZS_LL_BITS[lc];
+                const uint32_t t = b.read((int)(mlb + llb));                 // match-length then literal-length extra bits (<= 32)
+                const uint32_t mlen = ZS_ML_BASE[mc] + (llb >= 32 ? 0u : (t >> llb));
+                const uint32_t llen = ZS_LL_BASE[lc] + (t & ((1u << llb) - 1));
+                if (b.pos < 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                uint32_t off;
+                if (oc >= 2 || ovx + (1u << oc) > 3) {
+                    const uint64_t ov = (1ull << oc) + ovx;
+                    if (ov - 3 > 0xFFFFFFFFull) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                    off = (uint32_t)(ov - 3);
+                    z.rep2 = z.rep1; z.rep1 = z.rep0; z.rep0 = off;
                 } else {
-                    const uint32_t v = idx == 1 ? z.rep1 : (idx == 2 ? z.rep2 : z.rep0 - 1);
-                    if (v == 0) return CJ_ST_CORRUPT;
-                    if (idx > 1) z.rep2 = z.rep1;
-                    z.rep1 = z.rep0;
-                    z.rep0 = v;
-                    off = v;
+                    const uint32_t idx = (1u << oc) + ovx - 1 + (llen == 0 ? 1 : 0);
+                    if (idx == 0) {
+                        off = z.rep0;
+                    } else {
+                        const uint32_t v = idx == 1 ? z.rep1 : (idx == 2 ? z.rep2 : z.rep0 - 1);
+                        if (v == 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                        if (idx > 1) z.rep2 = z.rep1;
+                        z.rep1 = z.rep0;
+                        z.rep0 = v;
+                        off = v;
+                    }
                 }
+                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF bits in that order (<= 9 + 9 + 8)
+                    const uint32_t nl = (el >> 8) & 0xff, nm = (em >> 8) & 0xff, no = (eo >> 8) & 0xff;
+                    const uint32_t u = b.read((int)(nl + nm + no));
+                    sl = (el >> 16) + (u >> (nm + no));
+                    sm = (em >> 16) + ((u >> no) & ((1u << nm) - 1));
+                    so = (eo >> 16) + (u & ((1u << no) - 1));
+                    if (b.pos < 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                }
+                if (llen > lit_len - lp) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                if ((uint32_t)lane == k) { LL = llen; ML = mlen; OFF = off; LP = lp; }
+                lp += llen;
             }
-            if (i + 1 < nseq) {
-                sl = (el >> 16) + b.read((el >> 8) & 0xff);
-                sm = (em >> 16) + b.read((em >> 8) & 0xff);
-                so = (eo >> 16) + b.read((eo >> 8) & 0xff);
-                if (b.pos < 0) return CJ_ST_CORRUPT;
+            // ---- lane-parallel execution of those sequences (literals from the literal buffer, matches through the ring) ----
+            uint32_t left = cnt;
+            while (left) {
+                out.make_room();
+                const uint32_t k = exec_lanes<RULE_LEN, true>(out, left, LL, lit, LP, 0xFFFFFFFFu, ML, OFF, cap, lane);
+                if (k == left) break;
+                // element k did not pass the batch checks (too long for a batch, or invalid): serial path, exact status
+                const uint32_t jl = __shfl_sync(FULL, LL, k), jm = __shfl_sync(FULL, ML, k), jo = __shfl_sync(FULL, OFF, k), jp = __shfl_sync(FULL, LP, k);
+                if ((uint64_t)jl + jm > (uint64_t)(cap - out.op))
+                    return ((uint64_t)(out.op - block_start) + jl + jm > ZS_BLOCK_MAX) ? CJ_ST_CORRUPT : CJ_ST_DST_SMALL;
+                if (jl) out.put_literals_coherent(lit + jp, jl);
+                if (jo > out.op - out.base) return CJ_ST_OFFSET;
+                out.put_match(jo, jm);
+                const uint32_t sh = k + 1;  // drop the executed prefix: lane j takes over lane j+sh
+                LL = __shfl_down_sync(FULL, LL, sh); ML = __shfl_down_sync(FULL, ML, sh);
+                OFF = __shfl_down_sync(FULL, OFF, sh); LP = __shfl_down_sync(FULL, LP, sh);
+                left -= sh;
             }
-            if (llen > lit_len - lp) return CJ_ST_CORRUPT;
-            if ((uint64_t)llen + mlen > (uint64_t)(cap - out.op))
-                return ((uint64_t)(out.op - block_start) + llen + mlen > ZS_BLOCK_MAX) ? CJ_ST_CORRUPT : CJ_ST_DST_SMALL;
-            if (llen) out.put_literals_coherent(lit + lp, llen);
-            lp += llen;
-            if (off > out.op - out.base) return CJ_ST_OFFSET;
-            out.put_match(off, mlen);
+            if (derr) return derr;
+            if (out.op - block_start > ZS_BLOCK_MAX) return CJ_ST_CORRUPT;
         }
         if (b.pos != 0) return CJ_ST_CORRUPT;
     }
