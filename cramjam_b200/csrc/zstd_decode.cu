@@ -97,7 +97,13 @@ struct BackBits {
             }
             refill();
         }
-        return (uint32_t)((win >> (uint32_t)(lo - wbit)) & ((1ull << nb) - 1));
+        // 32-bit funnel shift over the two window halves instead of a 64-bit shift + mask
+        const uint32_t sft = (uint32_t)(lo - wbit);
+        const uint32_t w0 = (uint32_t)win, w1 = (uint32_t)(win >> 32);
+        const uint32_t v = (sft & 32) ? (w1 >> (sft & 31)) : __funnelshift_r(w0, w1, sft);
+        uint32_t r;
+        asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(nb));
+        return r;
     }
     __device__ __forceinline__ uint32_t read(int nb) {
         const uint32_t v = peek(nb);
@@ -420,20 +426,18 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
             int32_t derr = CJ_OK;  // a decode error stops the batch; the sequences before it still run first (their errors come first)
             uint32_t LL = 0, ML = 0, OFF = 0, LP = 0;
             for (uint32_t k = 0; k < cnt; k++) {
+                // table symbols are range-checked when the tables are built, so codes index the constant tables safely
                 const uint32_t el = z.ll.t[sl], eo = z.of.t[so], em = z.ml.t[sm];
                 const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
-                if (oc > 31 || lc > 35 || mc > 52) { derr = CJ_ST_CORRUPT; cnt = k; break; }
                 const uint32_t ovx = b.read((int)oc);                        // offset extra bits (<= 31)
                 const uint32_t mlb = ZS_ML_BITS[mc], llb = ZS_LL_BITS[lc];
                 const uint32_t t = b.read((int)(mlb + llb));                 // match-length then literal-length extra bits (<= 32)
-                const uint32_t mlen = ZS_ML_BASE[mc] + (llb >= 32 ? 0u : (t >> llb));
+                const uint32_t mlen = ZS_ML_BASE[mc] + (t >> llb);
                 const uint32_t llen = ZS_LL_BASE[lc] + (t & ((1u << llb) - 1));
-                if (b.pos < 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                bool bad = false;
                 uint32_t off;
-                if (oc >= 2 || ovx + (1u << oc) > 3) {
-                    const uint64_t ov = (1ull << oc) + ovx;
-                    if (ov - 3 > 0xFFFFFFFFull) { derr = CJ_ST_CORRUPT; cnt = k; break; }
-                    off = (uint32_t)(ov - 3);
+                if (oc >= 2) {
+                    off = (1u << oc) + ovx - 3;
                     z.rep2 = z.rep1; z.rep1 = z.rep0; z.rep0 = off;
                 } else {
                     const uint32_t idx = (1u << oc) + ovx - 1 + (llen == 0 ? 1 : 0);
@@ -441,7 +445,7 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
                         off = z.rep0;
                     } else {
                         const uint32_t v = idx == 1 ? z.rep1 : (idx == 2 ? z.rep2 : z.rep0 - 1);
-                        if (v == 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                        bad = v == 0;
                         if (idx > 1) z.rep2 = z.rep1;
                         z.rep1 = z.rep0;
                         z.rep0 = v;
@@ -454,9 +458,9 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
                     sl = (el >> 16) + (u >> (nm + no));
                     sm = (em >> 16) + ((u >> no) & ((1u << nm) - 1));
                     so = (eo >> 16) + (u & ((1u << no) - 1));
-                    if (b.pos < 0) { derr = CJ_ST_CORRUPT; cnt = k; break; }
                 }
-                if (llen > lit_len - lp) { derr = CJ_ST_CORRUPT; cnt = k; break; }
+                // every decode-side failure of a sequence is the same status, so one test per sequence is enough
+                if (bad || b.pos < 0 || llen > lit_len - lp) { derr = CJ_ST_CORRUPT; cnt = k; break; }
                 if ((uint32_t)lane == k) { LL = llen; ML = mlen; OFF = off; LP = lp; }
                 lp += llen;
             }
