@@ -3,6 +3,8 @@
 // Host-side plumbing only: context (device, stream, scratch arenas, pinned staging), batch
 // staging for CJ_HOST / CJ_PINNED callers, dispatch to the codec kernels.  No codec arithmetic
 // runs on the CPU here; if the CUDA device is missing every compute entry point fails loudly.
+#include <chrono>
+
 #include "internal.h"
 #include "synth.cuh"
 
@@ -137,13 +139,13 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
 }  // extern "C"
 
 // ---- kernel dispatch on a device-resident batch ------------------------------------------------
-static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params, int slot = 0) {
+static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params, int slot = 0, bool reset_counter = true) {
     if (b.n == 0) return CJ_OK;
     cudaError_t e;
     unsigned* counters = c->counters + (slot & 63);
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream);
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream, reset_counter);
         else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, counters, c->sm_count, c->stream);
         else if (codec == CJ_ZSTD) {
             int rc = c->z_lit.ensure(cj::zstd_scratch_bytes(c->sm_count, b.n));
@@ -153,7 +155,7 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
     } else {
         int accel = params && params->acceleration > 0 ? params->acceleration : 1;
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, accel, c->stream);
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, accel, c->stream, reset_counter);
         else { cj_set_error("codec %d has no device-resident batch encoder", codec); return CJ_E_INVALID_ARG; }
     }
     cudaEventRecord(c->ev1, c->stream);
@@ -199,7 +201,18 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
     memcpy(hq + 3 * n, bt->dst_cap, n * 8);
     uint64_t* dq = (uint64_t*)c->d_desc.p;
     CUDA_TRY(cudaMemcpyAsync(dq, hq, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, 64 * sizeof(unsigned), c->stream));
+    // Nothing but kernels may follow on the compute stream: a copy-engine operation here (counter memset, a small
+    // result copy) would queue behind the bulk transfers on that engine and stall the kernels with it.  The kernels
+    // therefore write dst_len / status straight into the pinned, device-mapped descriptor buffer.
     const int chunks = cj_ctx::PIPE;
+    static const bool trace_ev = getenv("CJ_TRACE") != nullptr;
+    cudaEvent_t tr0 = nullptr, tr_in[cj_ctx::PIPE] = {}, tr_k0[cj_ctx::PIPE] = {}, tr_k1[cj_ctx::PIPE] = {};
+    if (trace_ev) {
+        cudaEventCreate(&tr0);
+        for (int i = 0; i < chunks; i++) { cudaEventCreate(&tr_in[i]); cudaEventCreate(&tr_k0[i]); cudaEventCreate(&tr_k1[i]); }
+        cudaEventRecord(tr0, c->stream);
+    }
     size_t first[cj_ctx::PIPE + 1];
     for (int k = 0; k <= chunks; k++) first[k] = n * (size_t)k / chunks;
     // enqueue all input copies and kernels
@@ -209,23 +222,28 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
         const uint64_t lo = bt->src_off[a] - s_lo, hi = bt->src_off[b - 1] + bt->src_len[b - 1] - s_lo;
         CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->d_src.p + lo, hs + s_lo + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->s_h2d));
         CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        if (trace_ev) cudaEventRecord(tr_in[k], c->s_h2d);
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        if (trace_ev) cudaEventRecord(tr_k0[k], c->stream);
         cj::Batch bb;
         bb.n = (uint32_t)(b - a);
         bb.src_base = (const uint8_t*)c->d_src.p; bb.src_off = dq + a; bb.src_len = dq + n + a;
         bb.dst_base = (uint8_t*)c->d_dst.p; bb.dst_off = dq + 2 * n + a; bb.dst_cap = dq + 3 * n + a;
-        bb.dst_len = dq + 4 * n + a; bb.status = (int32_t*)(dq + 5 * n) + a;
-        if ((rc = run_device(c, codec, compress, bb, params, k))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(hq + 4 * n + a, dq + 4 * n + a, (b - a) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync((int32_t*)(hq + 5 * n) + a, (int32_t*)(dq + 5 * n) + a, (b - a) * 4, cudaMemcpyDeviceToHost, c->stream));
+        bb.dst_len = hq + 4 * n + a; bb.status = (int32_t*)(hq + 5 * n) + a;
+        if ((rc = run_device(c, codec, compress, bb, params, k, false))) return rc;
+        if (trace_ev) cudaEventRecord(tr_k1[k], c->stream);
         CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
     }
     // drain: as each chunk's kernel finishes, send its output home
+    static const bool trace = getenv("CJ_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     const uint64_t* dl = hq + 4 * n;
     for (int k = 0; k < chunks; k++) {
         const size_t a = first[k], b = first[k + 1];
         if (a == b) continue;
         CUDA_TRY(cudaEventSynchronize(c->ev_k[k]));
+        if (trace) fprintf(stderr, "[cj] chunk %d kernel done at %.2f ms\n", k, ms_now());
         bool tight = true;
         for (size_t i = a; i < b && tight; i++) tight = dl[i] == bt->dst_cap[i];
         if (tight) {
@@ -238,6 +256,16 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
     }
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (trace) fprintf(stderr, "[cj] all output home at %.2f ms\n", ms_now());
+    if (trace_ev) {
+        for (int i = 0; i < chunks; i++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, tr0, tr_in[i]); cudaEventElapsedTime(&b, tr0, tr_k0[i]); cudaEventElapsedTime(&d, tr0, tr_k1[i]);
+            fprintf(stderr, "[cj] gpu timeline chunk %d: h2d done %.2f  kernel start %.2f  kernel end %.2f ms\n", i, a, b, d);
+            cudaEventDestroy(tr_in[i]); cudaEventDestroy(tr_k0[i]); cudaEventDestroy(tr_k1[i]);
+        }
+        cudaEventDestroy(tr0);
+    }
     memcpy(bt->dst_len, hq + 4 * n, n * 8);
     memcpy(bt->status, hq + 5 * n, n * 4);
     return CJ_OK;

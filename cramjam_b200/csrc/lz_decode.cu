@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz_decode_kernel(
 }
 
 template <int CODEC, bool FAST>
-static cudaError_t launch_one(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_one(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
     const size_t smem = (size_t)DEC_SMEM_WARP * DEC_WARPS;
     auto k = lz_decode_kernel<CODEC, FAST>;
     static bool attr_done = false;
@@ -46,18 +46,20 @@ static cudaError_t launch_one(const Batch& b, unsigned* counter, int sm_count, c
     const int need = (int)((b.n + DEC_WARPS - 1) / DEC_WARPS);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
-    if (e != cudaSuccess) return e;
+    if (reset_counter) {  // the pinned-arena pipeline zeroes all of its counters once, up front, to keep copy engines off this stream
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
+        if (e != cudaSuccess) return e;
+    }
     k<<<grid, DEC_WARPS * 32, smem, stream>>>(b, counter);
     return cudaGetLastError();
 }
 
-cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream) {
+cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
     // CJ_DECODE_SERIAL=1 selects the generation-1 warp-serial kernel (kept for A/B measurements).
     static const bool serial = [] { const char* e = getenv("CJ_DECODE_SERIAL"); return e && e[0] == '1'; }();
     if (codec == CJ_LZ4_BLOCK)
-        return serial ? launch_one<CJ_LZ4_BLOCK, false>(b, counter, sm_count, stream) : launch_one<CJ_LZ4_BLOCK, true>(b, counter, sm_count, stream);
-    return serial ? launch_one<CJ_SNAPPY_RAW, false>(b, counter, sm_count, stream) : launch_one<CJ_SNAPPY_RAW, true>(b, counter, sm_count, stream);
+        return serial ? launch_one<CJ_LZ4_BLOCK, false>(b, counter, sm_count, stream, reset_counter) : launch_one<CJ_LZ4_BLOCK, true>(b, counter, sm_count, stream, reset_counter);
+    return serial ? launch_one<CJ_SNAPPY_RAW, false>(b, counter, sm_count, stream, reset_counter) : launch_one<CJ_SNAPPY_RAW, true>(b, counter, sm_count, stream, reset_counter);
 }
 
 }  // namespace cj

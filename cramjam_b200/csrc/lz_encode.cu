@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsi
 }
 
 template <int CODEC>
-static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
     const size_t smem = (size_t)ENC_HSIZE * 4 * ENC_WARPS;
     auto k = lz_encode_kernel<CODEC>;
     static bool attr_done = false;
@@ -222,15 +222,17 @@ static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, c
     const int need = (int)((b.n + ENC_WARPS - 1) / ENC_WARPS);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
-    if (e != cudaSuccess) return e;
+    if (reset_counter) {  // the pinned-arena pipeline zeroes all of its counters once, up front, to keep copy engines off this stream
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
+        if (e != cudaSuccess) return e;
+    }
     k<<<grid, ENC_WARPS * 32, smem, stream>>>(b, counter);
     return cudaGetLastError();
 }
 
-cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream) {
+cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream, bool reset_counter) {
     (void)acceleration;  // the greedy warp match finder has a single speed setting
-    return codec == CJ_LZ4_BLOCK ? launch_enc<CJ_LZ4_BLOCK>(b, counter, sm_count, stream) : launch_enc<CJ_SNAPPY_RAW>(b, counter, sm_count, stream);
+    return codec == CJ_LZ4_BLOCK ? launch_enc<CJ_LZ4_BLOCK>(b, counter, sm_count, stream, reset_counter) : launch_enc<CJ_SNAPPY_RAW>(b, counter, sm_count, stream, reset_counter);
 }
 
 }  // namespace cj

@@ -52,7 +52,7 @@ if len(sys.argv) > 5:
     acc = {name: [0, 0] for name, _, _ in ranges}; acc["other"] = [0, 0]
     for ln, (n, s) in agg.items():
         key = "other"
-        if ln and ln[0] == "lz_decode.cu":
+        if ln and ln[0] in ("lz_decode.cu", "lz_decode.cuh"):
             for name, lo, hi in ranges:
                 if lo <= ln[1] <= hi:
                     key = name; break
