@@ -344,12 +344,11 @@ struct InRing {
 template <int CODEC>
 __device__ __forceinline__ uint32_t elem_size(const InRing& in, uint32_t p) {
     const uint32_t n = in.n;
-    if (p >= n) return 0;
-    const uint32_t b0 = in.byte(p);
+    const uint32_t b0 = in.byte(p);  // p >= n reads stale ring bytes; the end-of-input tests below turn that into sz = 0
     uint32_t sz;
     if (CODEC == CJ_SNAPPY_RAW) {
         const uint32_t type = b0 & 3, L = b0 >> 2;
-        if (type == 0) sz = L < 60 ? L + 2 : (L == 60 ? in.byte(p + 1) + 3 : 0);
+        if (type == 0) sz = L < 60 ? L + 2 : 0;  // literals longer than 60 bytes carry their length in extra bytes: serial path
         else sz = type == 1 ? 2 : (type == 2 ? 3 : 0);
         if (p + sz > n) sz = 0;
     } else {
@@ -407,7 +406,9 @@ __device__ __forceinline__ void parse_window(const InRing& in, uint32_t& pp, uin
 // in global memory (re-read through L1/L2 with plain coherent loads) — one instruction stream serves all.
 __device__ __forceinline__ void lane_copy16(const uint8_t* gp, uint32_t dp, uint32_t nl) {
     const uint32_t mx = __reduce_max_sync(FULL, nl);
-    for (uint32_t b = 0; b < mx; b += 4) {
+#pragma unroll
+    for (uint32_t b = 0; b < 16; b += 4) {  // fully unrolled: constant offsets, warp-uniform early exit
+        if (b >= mx) break;
         uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
         if (b < nl) v0 = gp[b];
         if (b + 1 < nl) v1 = gp[b + 1];
@@ -527,8 +528,8 @@ __device__ __forceinline__ uint32_t exec_batch(const InRing& in, OutRing& out, u
             const uint32_t b1 = in.byte(p + 1), b2 = in.byte(p + 2);
             const uint32_t type = b0 & 3, L = b0 >> 2;
             if (type == 0) {
-                if (L < 60) { LL = L + 1; lsrc = p + 1; }
-                else { LL = b1 + 1; lsrc = p + 2; }
+                LL = L + 1;  // the lane-parallel path only sees one-byte literal tags (L < 60)
+                lsrc = p + 1;
             } else if (type == 1) {
                 ML = 4 + (L & 7);
                 off = ((b0 >> 5) << 8) | b1;
