@@ -330,6 +330,31 @@ def run_ours(args):
                 extras["lz4_block_decompress_GBps"] = EB * U / (ms_d * 1e6)
         extras["blocks"] = EB
         del eslots
+        # zstd level-3 frame decompress (BASELINE configs[3] shape, reduced count): frames made by the system libzstd on the host
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import syslibs as S
+            from concurrent.futures import ThreadPoolExecutor
+            if S.have_zstd:
+                ZF, ZU = 4096, 262144
+                zraw = raw[: ZF * ZU].cpu().numpy()
+                with ThreadPoolExecutor(os.cpu_count()) as ex:
+                    frames = list(ex.map(lambda i: S.zstd_compress(zraw[i * ZU:(i + 1) * ZU].tobytes(), 3), range(ZF)))
+                zl = np.array([len(f) for f in frames], dtype=np.uint64)
+                zo = np.zeros(ZF, dtype=np.uint64); zo[1:] = np.cumsum((zl[:-1] + np.uint64(15)) & ~np.uint64(15))
+                zsrc = np.zeros(int(zo[-1] + zl[-1]) + 64, dtype=np.uint8)
+                for i, f in enumerate(frames):
+                    zsrc[int(zo[i]):int(zo[i]) + len(f)] = np.frombuffer(f, dtype=np.uint8)
+                t_zsrc = torch.from_numpy(zsrc).to(dev)
+                t_zo, t_zl = i64(zo), i64(zl)
+                t_zdo, t_zdc = i64(np.arange(ZF, dtype=np.uint64) * ZU), i64(np.full(ZF, ZU, np.uint64))
+                ms_z = timed(lambda: ctx.decompress_batch(capi.ZSTD, capi.DEVICE, ZF, t_zsrc, t_zo, t_zl, out, t_zdo, t_zdc, t_dl, t_st), k=3)
+                assert int((t_st[:ZF] != 0).sum()) == 0 and bool(torch.equal(out[: ZF * ZU], raw[: ZF * ZU]))
+                extras["zstd_l3_frame_decompress_GBps"] = ZF * ZU / (ms_z * 1e6)
+                extras["zstd_frames"] = ZF
+                extras["zstd_ratio_libzstd_l3"] = ZF * ZU / float(zl.sum())
+        except Exception as e:  # extras never fail the headline line
+            extras["zstd_error"] = repr(e)[:200]
 
     # ---- CPU baseline beside it (rank 0 at N == 1 only; bounded sample) ----
     cpu = None
