@@ -131,7 +131,7 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
         return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16;
     }
     case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8;
-    case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18;  // >= ZSTD_compressBound for the raw-block frames this build emits
+    case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18;  // a block that does not shrink is stored raw: header + 3 bytes per block
     default: return 0;
     }
 }
@@ -156,6 +156,11 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     } else {
         int accel = params && params->acceleration > 0 ? params->acceleration : 1;
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, accel, c->stream, reset_counter);
+        else if (codec == CJ_ZSTD) {
+            int rc = c->z_enc.ensure(cj::zstd_enc_scratch_bytes(c->sm_count, b.n));
+            if (rc) return rc;
+            e = cj::launch_zstd_encode(b, counters, (uint8_t*)c->z_enc.p, c->sm_count, c->stream);
+        }
         else { cj_set_error("codec %d has no device-resident batch encoder", codec); return CJ_E_INVALID_ARG; }
     }
     cudaEventRecord(c->ev1, c->stream);
@@ -392,7 +397,7 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     }
     std::lock_guard<std::mutex> g(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
-    if (codec == CJ_SNAPPY_FRAMED || ((codec == CJ_LZ4_FRAME || codec == CJ_ZSTD) && compress))
+    if (codec == CJ_SNAPPY_FRAMED || (codec == CJ_LZ4_FRAME && compress))
         return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
     // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
     if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME && codec != CJ_ZSTD) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }

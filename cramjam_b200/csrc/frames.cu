@@ -721,73 +721,6 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
     return download_units(c, bt, where, dbase, dacc);
 }
 
-// ---- zstd compress: PLACEHOLDER — valid frames made of Raw_Blocks (ratio 1.0) ---------------------
-// The real level-3-class encoder (match finder + FSE/Huffman entropy stage) is the listed "next" row
-// (north_star names zstd *decode* only).  This keeps cramjam.zstd.compress and the
-// streaming Compressor usable and format-valid: single-segment frame, pledged Frame_Content_Size
-// (reference src/zstd.rs:45,61 passes the input size), Raw_Blocks of <= 128 KiB spliced on the device.
-int zstd_store_compress(cj_ctx* c, int where, const cj_batch* bt) {
-    const size_t n = bt->n;
-    std::vector<uint64_t> sbase;
-    int rc;
-    if ((rc = upload_units(c, bt, where, sbase))) return rc;
-    std::vector<uint64_t> dbase(n), total(n, 0);
-    Items hdr, body;
-    std::vector<uint8_t> hb;
-    size_t dacc = 0;
-    for (size_t i = 0; i < n; i++) {
-        dbase[i] = dacc;
-        bt->status[i] = CJ_OK;
-        const uint64_t L = bt->src_len[i];
-        uint8_t fh[16];
-        h_wr32(fh, 0xFD2FB528u);
-        size_t hl = 5;
-        if (L < 256) { fh[4] = 0x20; fh[5] = (uint8_t)L; hl = 6; }
-        else if (L < 65536 + 256) { fh[4] = 0x60; const uint32_t v = (uint32_t)(L - 256); fh[5] = (uint8_t)v; fh[6] = (uint8_t)(v >> 8); hl = 7; }
-        else if (L <= 0xFFFFFFFFull) { fh[4] = 0xA0; h_wr32(fh + 5, (uint32_t)L); hl = 9; }
-        else { fh[4] = 0xE0; memcpy(fh + 5, &L, 8); hl = 13; }
-        hdr.add(hb.size(), hl, dacc, 0);
-        hb.insert(hb.end(), fh, fh + hl);
-        uint64_t pos = hl;
-        uint64_t p = 0;
-        do {
-            const uint64_t bl = std::min<uint64_t>(128 * 1024, L - p);
-            const bool last = p + bl >= L;
-            const uint32_t bh = (uint32_t)(last ? 1 : 0) | (uint32_t)(bl << 3);
-            uint8_t b3[3] = {(uint8_t)bh, (uint8_t)(bh >> 8), (uint8_t)(bh >> 16)};
-            hdr.add(hb.size(), 3, dacc + pos, 0);
-            hb.insert(hb.end(), b3, b3 + 3);
-            if (bl) body.add(sbase[i] + p, bl, dacc + pos + 3, 0);
-            pos += 3 + bl;
-            p += bl;
-        } while (p < L);
-        total[i] = pos;
-        if (pos > bt->dst_cap[i]) bt->status[i] = CJ_ST_DST_SMALL;
-        dacc += cj_align16((size_t)pos);
-    }
-    if ((rc = c->f_ddst.ensure(dacc + hb.size() + 128))) return rc;
-    const size_t blob_off = dacc;
-    if ((rc = c->f_hdst.ensure(hb.size() + 64))) return rc;
-    memcpy(c->f_hdst.p, hb.data(), hb.size());
-    CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->f_ddst.p + blob_off, c->f_hdst.p, hb.size(), cudaMemcpyHostToDevice, c->stream));
-    auto splice = [&](const Items& it, const uint8_t* sb, uint64_t sadd) -> int {
-        if (!it.size()) return CJ_OK;
-        Items t = it;
-        for (auto& v : t.so) v += sadd;
-        DevItems d;
-        int r = upload_items(c, t, c->f_ddesc, c->f_hdesc, &d);
-        if (r) return r;
-        r = copy_units(c, (uint32_t)t.size(), sb, d.so, d.sl, (uint8_t*)c->f_ddst.p, d.dof);
-        if (r) return r;
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        return CJ_OK;
-    };
-    if ((rc = splice(hdr, (const uint8_t*)c->f_ddst.p, blob_off))) return rc;
-    if ((rc = splice(body, (const uint8_t*)c->f_dsrc.p, 0))) return rc;
-    for (size_t i = 0; i < n; i++) bt->dst_len[i] = bt->status[i] == CJ_OK ? total[i] : 0;
-    return download_units(c, bt, where, dbase, dacc);
-}
-
 }  // namespace
 
 int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
@@ -809,7 +742,6 @@ int frames_compress(cj_ctx* c, int codec, int where, const cj_batch* bt, const c
     if (bt->n == 0) return CJ_OK;
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_compress(c, where, bt);
     if (codec == CJ_LZ4_FRAME) return lz4f_compress(c, where, bt, params);
-    if (codec == CJ_ZSTD) return zstd_store_compress(c, where, bt);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }

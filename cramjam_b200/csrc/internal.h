@@ -31,6 +31,8 @@ cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int s
 cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
 cudaError_t launch_zstd_decode(const Batch& b, unsigned* counter, uint8_t* lit_scratch, int sm_count, cudaStream_t stream);
 size_t zstd_scratch_bytes(int sm_count, uint32_t n);
+cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, cudaStream_t stream);
+size_t zstd_enc_scratch_bytes(int sm_count, uint32_t n);
 cudaError_t launch_copy_units(uint32_t n, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* len, uint8_t* dst_base,
                               const uint64_t* dst_off, int sm_count, cudaStream_t stream);
 cudaError_t launch_synth(uint8_t* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, cudaStream_t stream);
@@ -83,13 +85,13 @@ struct cj_ctx {
     std::mutex mu;
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)
-    Scratch z_lit;                                                     // zstd per-warp literal buffers (device)
+    Scratch z_lit, z_enc;                                              // zstd per-warp literal buffers / encoder scratch (device)
     cj_ctx() {
         h_src.pinned = h_dst.pinned = h_desc.pinned = true;
         f_hsrc.pinned = f_hdst.pinned = f_hdesc.pinned = true;
     }
     void release_all() {
-        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit};
+        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc};
         for (Scratch* s : all) s->release();
     }
 };

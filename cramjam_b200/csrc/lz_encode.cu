@@ -16,24 +16,11 @@
 // compare; the matches of a step are then taken greedily in position order: the warp extends each
 // one 32 bytes per ballot, emits the pending literal run (lane-parallel byte copy) and the copy
 // element(s), and skips the lanes the match covered.
-#include "common.cuh"
+#include "lz_match.cuh"
 
 namespace cj {
 
-constexpr int ENC_HBITS = 12;
-constexpr int ENC_HSIZE = 1 << ENC_HBITS;
 constexpr int ENC_WARPS = 4;
-constexpr uint32_t ENC_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t ENC_MAXOFF = 65535;
-
-__device__ __forceinline__ uint32_t load32u(const uint8_t* p) {  // unaligned little-endian 32-bit load
-    const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(p - a);
-    const uint32_t lo = __ldg(w);
-    if (a == 0) return lo;
-    const uint32_t hi = __ldg(w + 1);
-    return __funnelshift_r(lo, hi, a * 8);
-}
 
 struct EncOut {
     uint8_t* dst;
@@ -134,51 +121,15 @@ __device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uin
     const uint32_t match_limit = CODEC == CJ_SNAPPY_RAW ? n : (n >= 5 ? n - 5 : 0);
     uint32_t anchor = 0;
     if (start_limit > 0) {
-        for (uint32_t i = lane; i < ENC_HSIZE / 4; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(ENC_EMPTY, ENC_EMPTY, ENC_EMPTY, ENC_EMPTY);
-        __syncwarp();
-        uint32_t p = 0;
-        while (p < start_limit) {
-            const uint32_t pos = p + lane;
-            const bool valid = pos < start_limit;
-            uint32_t v = 0, h = 0, cand = ENC_EMPTY;
-            if (valid) {
-                v = load32u(src + pos);
-                h = (v * 0x9E3779B1u) >> (32 - ENC_HBITS);
-                cand = table[h];
+        match_table_reset(table, lane);
+        anchor = find_matches(src, 0, start_limit, match_limit, table, lane, [&](uint32_t lit_at, uint32_t ll, uint32_t off, uint32_t ml) {
+            if (CODEC == CJ_SNAPPY_RAW) {
+                snappy_emit_literal(o, src + lit_at, ll);
+                snappy_emit_copy(o, off, ml);
+            } else {
+                lz4_emit_sequence(o, src + lit_at, ll, off, ml);
             }
-            __syncwarp();
-            const uint32_t grp = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-            if (valid && lane == 31 - __clz(grp)) table[h] = pos;  // highest position of the bucket wins
-            __syncwarp();
-            const bool ok = valid && cand != ENC_EMPTY && pos - cand <= ENC_MAXOFF && load32u(src + cand) == v;
-            uint32_t mm = __ballot_sync(FULL, ok);
-            if (anchor > p) mm &= anchor - p >= 32 ? 0u : ~((1u << (anchor - p)) - 1);  // lanes covered by the previous match
-            while (mm) {
-                const int i = __ffs(mm) - 1;
-                const uint32_t mpos = p + i;
-                const uint32_t c = __shfl_sync(FULL, cand, i);
-                // extend the match, 32 bytes per ballot
-                uint32_t len = 4;
-                const uint32_t maxlen = match_limit - mpos;
-                for (;;) {
-                    const uint32_t k = len + lane;
-                    const bool eq = k < maxlen && __ldg(src + c + k) == __ldg(src + mpos + k);
-                    const uint32_t ne = __ballot_sync(FULL, !eq);
-                    if (ne) { len += __ffs(ne) - 1; break; }
-                    len += 32;
-                }
-                if (CODEC == CJ_SNAPPY_RAW) {
-                    snappy_emit_literal(o, src + anchor, mpos - anchor);
-                    snappy_emit_copy(o, mpos - c, len);
-                } else {
-                    lz4_emit_sequence(o, src + anchor, mpos - anchor, mpos - c, len);
-                }
-                anchor = mpos + len;
-                const uint32_t covered = anchor - p;  // lanes below this were swallowed by the match
-                mm = covered >= 32 ? 0u : mm & ~((1u << covered) - 1);
-            }
-            p = max(p + 32, anchor);
-        }
+        });
     }
     if (CODEC == CJ_SNAPPY_RAW) snappy_emit_literal(o, src + anchor, n - anchor);
     else lz4_emit_sequence(o, src + anchor, n - anchor, 0, 0);

@@ -81,3 +81,38 @@ def test_synthetic_256k_frames_level3():
     units = [S.zstd_compress(b, 3) for b in blocks]
     outs, st = ctx().run_host_units(capi.ZSTD, False, units, [U] * n)
     assert (st == 0).all() and outs == blocks
+
+
+# ---- encoder (reference src/zstd.rs:37-64; SURVEY 8f "next" row, first real encoder) ----
+def _zcompress(units):
+    return ctx().run_host_units(capi.ZSTD, True, units, [capi.lib().cj_compress_bound(capi.ZSTD, len(u)) for u in units])
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+def test_zstd_encode_is_valid_for_libzstd_oracle_and_own_decoder():
+    outs, st = _zcompress(CASES)
+    assert (st == 0).all()
+    for d, c in zip(CASES, outs):
+        assert c[:4] == b"\x28\xb5\x2f\xfd"
+        assert S.zstd_decompress(c, len(d)) == d, len(d)       # libzstd accepts and reproduces
+        assert O.zstd_len(c) == len(d)                          # pledged content size in the header
+        assert O.zstd_decompress(c) == d
+    back, st2 = ctx().run_host_units(capi.ZSTD, False, outs, [len(d) for d in CASES])
+    assert (st2 == 0).all() and back == CASES
+
+
+def test_zstd_encode_compresses_and_is_deterministic():
+    n, U = 64, 262144
+    data = capi.synth_host(n * 4, 65536, seed=3)
+    units = [data[i * U:(i + 1) * U].tobytes() for i in range(n)]
+    a, st = _zcompress(units)
+    b, _ = _zcompress(units)
+    assert (st == 0).all() and a == b
+    ratio = n * U / sum(len(c) for c in a)
+    assert ratio > 1.6, ratio                                   # LZ4-class (raw literals, predefined FSE tables)
+    for u, c in zip(units[::8], a[::8]):
+        assert O.zstd_decompress(c) == u
+    outs, st = _zcompress([corpus.text(5000, 1)])
+    d = corpus.text(5000, 1)
+    small, st = ctx().run_host_units(capi.ZSTD, True, [d], [10])
+    assert st[0] == 5                                           # DST_SMALL
