@@ -45,3 +45,28 @@ for _ in range(K):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print(f"GPU zstd decode {ms:.2f} ms/batch  {n*U/ms/1e6:.1f} GB/s uncompressed ({n} x 256 KiB frames)")
+# GPU zstd compress of the same 256 KiB units
+bound = capi.lib().cj_compress_bound(capi.ZSTD, U)
+slot = (bound + 15) // 16 * 16
+t_raw = torch.from_numpy(data[: n * U]).to(dev)
+t_cmp = torch.zeros(n * slot, dtype=torch.uint8, device=dev)
+t_co, t_cc = i64(np.arange(n, dtype=np.uint64) * slot), i64(np.full(n, slot, np.uint64))
+t_cl = torch.zeros(n, dtype=torch.int64, device=dev)
+for _ in range(2):
+    c.compress_batch(capi.ZSTD, capi.DEVICE, n, t_raw, t_do, t_dc, t_cmp, t_co, t_cc, t_cl, t_st)
+torch.cuda.synchronize()
+assert (t_st == 0).all()
+e0.record()
+for _ in range(K):
+    c.compress_batch(capi.ZSTD, capi.DEVICE, n, t_raw, t_do, t_dc, t_cmp, t_co, t_cc, t_cl, t_st)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+print(f"GPU zstd compress {ms:.2f} ms/batch  {n*U/ms/1e6:.1f} GB/s uncompressed  ratio {n*U/float(t_cl.sum().item()):.3f}")
+c.decompress_batch(capi.ZSTD, capi.DEVICE, n, t_cmp, t_co, t_cl, t_dst.zero_(), t_do, t_dc, t_dl, t_st)
+torch.cuda.synchronize()
+assert (t_st == 0).all() and torch.equal(t_dst, t_raw)
+e0.record()
+for _ in range(K):
+    c.decompress_batch(capi.ZSTD, capi.DEVICE, n, t_cmp, t_co, t_cl, t_dst, t_do, t_dc, t_dl, t_st)
+e1.record(); torch.cuda.synchronize()
+print(f"GPU zstd decode of GPU-made frames {n*U/(e0.elapsed_time(e1)/K)/1e6:.1f} GB/s")
