@@ -356,6 +356,40 @@ def run_ours(args):
         except Exception as e:  # extras never fail the headline line
             extras["zstd_error"] = repr(e)[:200]
 
+    # ---- N > 1 extra: the "batch lives on rank 0" mode — NCCL point-to-point scatter of compressed ranges,
+    #      per-rank decode, gather of the outputs (north_star: NCCL only for the trivial scatter/gather) ----
+    if world > 1 and not args.no_extras:
+        from cramjam_b200.sharding import partition_units, scatter_units, gather_units
+        SB = 16384                                   # blocks held by rank 0 for this leg (1 GiB uncompressed)
+        ranges = partition_units(np.full(SB, U), world)
+        s_lo, s_hi = ranges[rank]
+        k = s_hi - s_lo
+        t_so = i64(np.arange(max(k, 1), dtype=np.uint64) * U)
+        t_sc = i64(np.full(max(k, 1), U, np.uint64))
+        t_sdl = torch.zeros(max(k, 1), dtype=torch.int64, device=dev)
+        t_sst = torch.zeros(max(k, 1), dtype=torch.int32, device=dev)
+        sout = torch.empty(max(k, 1) * U, dtype=torch.uint8, device=dev)
+
+        def scatter_decode_gather():
+            pay = comp if rank == 0 else None
+            local, loff, llen = scatter_units(pay, coff[:SB] if rank == 0 else None, clen[:SB] if rank == 0 else None, ranges, 0, dev)
+            if k:
+                ctx.decompress_batch(capi.SNAPPY_RAW, capi.DEVICE, k, local, i64(loff), i64(llen), sout, t_so, t_sc, t_sdl, t_sst)
+            torch.cuda.current_stream().synchronize()
+            return gather_units(sout, np.full(k, U, np.uint64), ranges, 0)
+
+        res = scatter_decode_gather()
+        if rank == 0:
+            assert bool(torch.equal(res[0], raw[: SB * U])), "scatter/decode/gather output differs"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            scatter_decode_gather()
+        barrier()
+        ms_sg = max_over_ranks(1e3 * (time.perf_counter() - t0) / 3)
+        extras = {"scatter_decode_gather_GBps": SB * U / (ms_sg * 1e6), "scatter_blocks": SB,
+                  "note": "rank 0 holds the batch; NCCL p2p scatter of compressed ranges + gather of outputs; bounded by rank 0's NVLink ingress"}
+
     # ---- CPU baseline beside it (rank 0 at N == 1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1:
