@@ -666,14 +666,16 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
     size_t dacc = 0, k = 0;
     for (size_t i = 0; i < n; i++) {
         dbase[i] = dacc;
-        uint8_t fh[7];
+        uint8_t fh[15];
         h_wr32(fh, 0x184D2204u);
-        fh[4] = 0x40 | 0x20 | 0x04;  // version 01, independent blocks, content checksum
-        fh[5] = 0x40;                // 64 KiB blocks
-        fh[6] = (uint8_t)(h_xxh32(fh + 4, 2) >> 8);
-        hdr.add(hb.size(), 7, dacc, 0);
-        hb.insert(hb.end(), fh, fh + 7);
-        uint64_t pos = 7;
+        fh[4] = 0x40 | 0x20 | 0x08 | 0x04;  // version 01, independent blocks, content size, content checksum
+        fh[5] = 0x40;                       // 64 KiB blocks
+        const uint64_t csize = bt->src_len[i];
+        memcpy(fh + 6, &csize, 8);
+        fh[14] = (uint8_t)(h_xxh32(fh + 4, 10) >> 8);
+        hdr.add(hb.size(), 15, dacc, 0);
+        hb.insert(hb.end(), fh, fh + 15);
+        uint64_t pos = 15;
         for (uint64_t p = 0; p < bt->src_len[i]; p += 65536, k++) {
             const uint64_t L = ch.sl[k];
             if (cst[k] != CJ_OK) bt->status[i] = cst[k];
@@ -751,17 +753,19 @@ int frames_compress(cj_ctx* c, int codec, int where, const cj_batch* bt, const c
 // ================================================================================================
 // Size helpers on HOST memory (header parsing only)
 // ================================================================================================
-static int lz4f_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact) {
+int cj_lz4f_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std::vector<cj_frame_info>* frames) {
     size_t p = 0, tot = 0;
     *exact = true;
     while (p < n) {
         if (n - p < 4) return CJ_ST_TRUNCATED;
         uint32_t magic; memcpy(&magic, s + p, 4);
+        const size_t frame_at = p;
         if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {
             if (n - p < 8) return CJ_ST_TRUNCATED;
             uint32_t sz; memcpy(&sz, s + p + 4, 4);
             if (sz > n - p - 8) return CJ_ST_TRUNCATED;
             p += 8 + sz;
+            if (frames) frames->push_back({frame_at, p - frame_at, 0, true});
             continue;
         }
         if (magic != 0x184D2204u) return CJ_ST_HEADER;
@@ -791,12 +795,12 @@ static int lz4f_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact)
         }
         if (csum) { if (n - p < 4) return CJ_ST_TRUNCATED; p += 4; }
         tot += csize ? (size_t)content : frame_tot;
+        if (frames) frames->push_back({frame_at, p - frame_at, csize ? (size_t)content : frame_tot, (bool)csize});
     }
     *out = tot;
     return CJ_OK;
 }
 
-int cj_zstd_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact);  // zstd_decode.cu
 
 static int decompressed_bound(cj_codec codec, const void* src, size_t n, size_t* out, bool want_exact) {
     if (!out || (!src && n)) return CJ_E_INVALID_ARG;
@@ -822,8 +826,8 @@ static int decompressed_bound(cj_codec codec, const void* src, size_t n, size_t*
         *out = n * 255;  // LZ4's maximum expansion; callers normally know the size (prefix / output_len)
         exact = false;
         break;
-    case CJ_LZ4_FRAME: st = lz4f_bound_host(s, n, out, &exact); break;
-    case CJ_ZSTD: st = cj_zstd_bound_host(s, n, out, &exact); break;
+    case CJ_LZ4_FRAME: st = cj_lz4f_walk_host(s, n, out, &exact, nullptr); break;
+    case CJ_ZSTD: st = cj_zstd_walk_host(s, n, out, &exact, nullptr); break;
     default: return CJ_E_INVALID_ARG;
     }
     if (st != CJ_OK) {

@@ -96,6 +96,15 @@ struct cj_ctx {
     }
 };
 
+// One frame of a (possibly concatenated) LZ4F / zstd stream, found by the host-side header walk.
+struct cj_frame_info {
+    size_t offset, size;   // position and length of the frame inside the stream
+    size_t content;        // decompressed size (exact if `known`, else an upper bound); 0 for skippable frames
+    bool known;
+};
+int cj_lz4f_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std::vector<cj_frame_info>* frames);
+int cj_zstd_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std::vector<cj_frame_info>* frames);
+
 // api.cu: run a block-codec batch whose descriptors and payload already live on the device (caller holds ctx->mu).
 int cj_run_device_batch(cj_ctx* c, int codec, bool compress, const cj::Batch& b, const cj_params* params);
 

@@ -687,7 +687,7 @@ cudaError_t launch_zstd_decode(const Batch& b, unsigned* counter, uint8_t* lit_s
 }  // namespace cj
 
 // ---- host-side header walk: decompressed size / bound (no payload byte is interpreted) ----
-int cj_zstd_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact) {
+int cj_zstd_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std::vector<cj_frame_info>* frames) {
     size_t p = 0, tot = 0;
     *exact = true;
     while (p < n) {
@@ -697,6 +697,7 @@ int cj_zstd_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact) {
             if (n - p < 8) return CJ_ST_TRUNCATED;
             uint32_t sz; memcpy(&sz, s + p + 4, 4);
             if (sz > n - p - 8) return CJ_ST_TRUNCATED;
+            if (frames) frames->push_back({p, (size_t)8 + sz, 0, true});
             p += 8 + sz;
             continue;
         }
@@ -739,6 +740,7 @@ int cj_zstd_bound_host(const uint8_t* s, size_t n, size_t* out, bool* exact) {
         if (fhd & 4) { if (n - q < 4) return CJ_ST_TRUNCATED; q += 4; }
         if (fsz) tot += (size_t)fcs;
         else { tot += frame_tot; *exact = false; }
+        if (frames) frames->push_back({p, q - p, fsz ? (size_t)fcs : frame_tot, fsz != 0});
         p = q;
     }
     *out = tot;
