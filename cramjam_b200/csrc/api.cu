@@ -210,7 +210,11 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
     // Nothing but kernels may follow on the compute stream: a copy-engine operation here (counter memset, a small
     // result copy) would queue behind the bulk transfers on that engine and stall the kernels with it.  The kernels
     // therefore write dst_len / status straight into the pinned, device-mapped descriptor buffer.
-    const int chunks = cj_ctx::PIPE;
+    static const int chunks = [] {
+        const char* e = getenv("CJ_PIPE_CHUNKS");
+        const int v = e ? atoi(e) : 16;
+        return v < 1 ? 1 : (v > cj_ctx::PIPE ? cj_ctx::PIPE : v);
+    }();
     static const bool trace_ev = getenv("CJ_TRACE") != nullptr;
     cudaEvent_t tr0 = nullptr, tr_in[cj_ctx::PIPE] = {}, tr_k0[cj_ctx::PIPE] = {}, tr_k1[cj_ctx::PIPE] = {};
     if (trace_ev) {

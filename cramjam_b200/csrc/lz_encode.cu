@@ -8,7 +8,7 @@
 // so the match finder is designed for the GPU, not transliterated.
 //
 // Execution model: persistent grid, one warp per block, atomic work queue.  Per warp a 4096-entry
-// hash table of 32-bit positions lives in shared memory.  The warp hashes 32 consecutive positions
+// hash table of 16-bit position slots lives in shared memory (8 KiB; lz_match.cuh).  The warp hashes 32 consecutive positions
 // per step (one per lane), looks all of them up, then inserts them — when several lanes share a
 // hash bucket the highest position wins, chosen with __match_any_sync so the result never depends
 // on store ordering (the encoder is deterministic; tests/test_variants.py:281 needs
@@ -92,8 +92,95 @@ __device__ __forceinline__ void lz4_emit_sequence(EncOut& o, const uint8_t* __re
     }
 }
 
+// ---- emitter handed to find_matches -------------------------------------------------------------
+// window(): all matches of one 32-position step at once.  Every chosen lane sizes its own element pair
+// (literal run + copy / LZ4 sequence), a warp prefix sum places the pairs, the lane writes its own header
+// bytes, and every literal position of the step stores its byte (already in the lane's register) where its
+// run lands — no per-match serial work, no reload of literal bytes.  Steps holding anything that needs more
+// than one header byte per length (or several copy elements) fall back to serial(), one match at a time.
 template <int CODEC>
-__device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, uint32_t* table, int lane, uint32_t* produced) {
+struct BlockEmitter {
+    EncOut& o;
+    const uint8_t* __restrict__ src;
+
+    __device__ __forceinline__ void serial(uint32_t lit_at, uint32_t ll, uint32_t off, uint32_t ml) {
+        if (CODEC == CJ_SNAPPY_RAW) {
+            snappy_emit_literal(o, src + lit_at, ll);
+            snappy_emit_copy(o, off, ml);
+        } else {
+            lz4_emit_sequence(o, src + lit_at, ll, off, ml);
+        }
+    }
+
+    __device__ __forceinline__ bool window(const uint8_t* __restrict__, uint32_t p, uint32_t v, uint32_t anchor, uint32_t sel, uint32_t mlen,
+                                           uint32_t off) {
+        const int lane = o.lane;
+        const bool me = (sel >> lane) & 1;
+        const uint32_t below = sel & ((1u << lane) - 1);
+        const uint32_t pe = __shfl_sync(FULL, p + lane + mlen, below ? 31 - __clz(below) : 0);
+        const uint32_t prev_end = below ? pe : anchor;  // where this lane's literal run starts
+        const uint32_t ll = me ? p + lane - prev_end : 0u;
+        uint32_t lhdr, tail;  // bytes before / after the literals
+        bool simple;
+        if (CODEC == CJ_SNAPPY_RAW) {
+            simple = ll <= 60 && mlen <= 64;
+            lhdr = ll ? 1 : 0;
+            tail = (mlen < 12 && off < 2048) ? 2 : 3;
+        } else {
+            simple = ll < 15 + 255 && mlen - 4 < 15 + 255;
+            lhdr = ll >= 15 ? 2 : 1;
+            tail = mlen - 4 >= 15 ? 3 : 2;
+        }
+        if (__any_sync(FULL, me && !simple)) return false;
+        const uint32_t size = me ? lhdr + ll + tail : 0u;
+        uint32_t incl = size;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        uint8_t* dst = o.dst;
+        const uint32_t ob = o.op + incl - size;  // where this lane's pair starts
+        const uint32_t lb = ob + lhdr;           // ... and its literals
+        if (me) {
+            uint8_t* c = dst + lb + ll;
+            if (CODEC == CJ_SNAPPY_RAW) {
+                if (ll) dst[ob] = (uint8_t)((ll - 1) << 2);
+                if (tail == 2) {
+                    c[0] = (uint8_t)(1u | ((mlen - 4) << 2) | ((off >> 8) << 5));
+                    c[1] = (uint8_t)off;
+                } else {
+                    c[0] = (uint8_t)(2u | ((mlen - 1) << 2));
+                    c[1] = (uint8_t)off;
+                    c[2] = (uint8_t)(off >> 8);
+                }
+            } else {
+                const uint32_t mc = mlen - 4;
+                dst[ob] = (uint8_t)((min(ll, 15u) << 4) | min(mc, 15u));
+                if (ll >= 15) dst[ob + 1] = (uint8_t)(ll - 15);
+                c[0] = (uint8_t)off;
+                c[1] = (uint8_t)(off >> 8);
+                if (mc >= 15) c[2] = (uint8_t)(mc - 15);
+            }
+        }
+        // literal positions of this step: not inside a match, and a chosen match follows
+        const uint32_t above = sel >> lane;
+        const int k = above ? lane + __ffs(above) - 1 : 0;
+        const uint32_t k_lb = __shfl_sync(FULL, lb, k), k_pe = __shfl_sync(FULL, prev_end, k);
+        const uint32_t pos = p + lane;
+        if (above && !me && pos >= k_pe) dst[k_lb + (pos - k_pe)] = (uint8_t)v;
+        if (anchor < p) {  // the first run began in an earlier step: those bytes come from memory
+            const uint32_t f_lb = __shfl_sync(FULL, lb, __ffs(sel) - 1);
+            for (uint32_t i = lane; i < p - anchor; i += 32) dst[f_lb + i] = __ldg(src + anchor + i);
+        }
+        o.op += total;
+        return true;
+    }
+};
+
+template <int CODEC>
+__device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, enc_slot_t* table, int lane, uint32_t* produced) {
     *produced = 0;
     const uint64_t bound = CODEC == CJ_SNAPPY_RAW ? 32ull + n + n / 6 : (uint64_t)n + n / 255 + 16;
     if (CODEC == CJ_LZ4_BLOCK && n > 0x7E000000u) return CJ_ST_TOO_BIG;
@@ -122,14 +209,8 @@ __device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uin
     uint32_t anchor = 0;
     if (start_limit > 0) {
         match_table_reset(table, lane);
-        anchor = find_matches(src, 0, start_limit, match_limit, table, lane, [&](uint32_t lit_at, uint32_t ll, uint32_t off, uint32_t ml) {
-            if (CODEC == CJ_SNAPPY_RAW) {
-                snappy_emit_literal(o, src + lit_at, ll);
-                snappy_emit_copy(o, off, ml);
-            } else {
-                lz4_emit_sequence(o, src + lit_at, ll, off, ml);
-            }
-        });
+        BlockEmitter<CODEC> em{o, src};
+        anchor = find_matches(src, 0, start_limit, match_limit, table, lane, em);
     }
     if (CODEC == CJ_SNAPPY_RAW) snappy_emit_literal(o, src + anchor, n - anchor);
     else lz4_emit_sequence(o, src + anchor, n - anchor, 0, 0);
@@ -142,7 +223,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsi
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t* table = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * ENC_HSIZE;
+    enc_slot_t* table = reinterpret_cast<enc_slot_t*>(smem) + (size_t)warp * ENC_HSIZE;
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
         if (u >= b.n) break;
@@ -161,15 +242,18 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsi
 
 template <int CODEC>
 static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
-    const size_t smem = (size_t)ENC_HSIZE * 4 * ENC_WARPS;
+    const size_t smem = ENC_TABLE_BYTES * ENC_WARPS;
     auto k = lz_encode_kernel<CODEC>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ENC_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ < 1 ? 1 : occ;
     }
-    int grid = sm_count * 3;
+    int grid = sm_count * ctas_per_sm;  // persistent: every resident CTA slot, units handed out by the atomic queue
     const int need = (int)((b.n + ENC_WARPS - 1) / ENC_WARPS);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;

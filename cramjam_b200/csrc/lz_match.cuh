@@ -11,8 +11,14 @@ namespace cj {
 
 constexpr int ENC_HBITS = 12;
 constexpr int ENC_HSIZE = 1 << ENC_HBITS;
-constexpr uint32_t ENC_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t ENC_MAXOFF = 65535;
+// A table slot keeps the low 16 bits of a position.  The candidate is rebuilt as pos - ((pos - slot) & 0xFFFF):
+// the most recent position congruent to the slot, at most 65535 bytes back (the LZ4 / Snappy-2 / window limit
+// all three encoders share).  There is no "empty" value: a zeroed table proposes the 64 KiB-aligned base, and
+// every candidate is verified by a 4-byte compare, so a stale or never-written slot only costs a failed compare.
+// Halving the slot size doubles the warps an SM can hold (8 KiB instead of 16 KiB of shared memory per warp).
+using enc_slot_t = uint16_t;
+constexpr size_t ENC_TABLE_BYTES = (size_t)ENC_HSIZE * sizeof(enc_slot_t);
 
 __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {  // unaligned little-endian 32-bit load
     const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
@@ -23,54 +29,107 @@ __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {  // unaligned li
     return __funnelshift_r(lo, hi, a * 8);
 }
 
-__device__ __forceinline__ void match_table_reset(uint32_t* table, int lane) {
-    for (uint32_t i = lane; i < ENC_HSIZE / 4; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(ENC_EMPTY, ENC_EMPTY, ENC_EMPTY, ENC_EMPTY);
+__device__ __forceinline__ void match_table_reset(enc_slot_t* table, int lane) {
+    for (uint32_t i = lane; i < ENC_TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 }
 
 // Scans src[begin, end): positions in [begin, start_limit) may start a match, a match may not pass
-// match_limit.  For every match taken, emit(anchor, literal_len, offset, match_len) is called warp-uniformly.
-// Returns the position where the trailing literal run starts.
-template <class Emit>
+// match_limit (start_limit <= match_limit - 3).  Returns the position where the trailing literal run starts.
+//
+// Per step of 32 positions the warp pays ONE dependent round trip to L1/L2: the 4-byte words of the next 32
+// positions are prefetched while the current ones are processed, and every lane that finds a verified
+// candidate extends its own match to 12 bytes right away (the words on the position side come from the
+// neighbouring lanes' registers by shuffle).  84 % of the matches of the bench corpus are <= 12 bytes and
+// need nothing more; longer ones are extended by the whole warp, 32 bytes per ballot.  The matches of a step
+// are chosen greedily in position order (registers only), then handed to the emitter together:
+//   em.window(src, p, v, anchor, sel, mlen, off)  all matches of the step at once, lane i of `sel` holding match
+//                                              (p + i, mlen, off); v = the lane's 4-byte word (its low byte is
+//                                              src[p + lane]); anchor = start of the pending literal run.
+//                                              Returns false if it wants the step one match at a time instead:
+//   em.serial(anchor, literal_len, offset, match_len)  warp-uniform.
+template <class Emitter>
 __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src, uint32_t begin, uint32_t start_limit, uint32_t match_limit,
-                                                 uint32_t* table, int lane, Emit&& emit) {
+                                                 enc_slot_t* table, int lane, Emitter& em) {
     uint32_t anchor = begin;
     uint32_t p = begin;
+    uint32_t v = p + lane < start_limit ? load32u(src + p + lane) : 0u;
     while (p < start_limit) {
         const uint32_t pos = p + lane;
         const bool valid = pos < start_limit;
-        uint32_t v = 0, h = 0, cand = ENC_EMPTY;
-        if (valid) {
-            v = load32u(src + pos);
-            h = (v * 0x9E3779B1u) >> (32 - ENC_HBITS);
-            cand = table[h];
-        }
+        const uint32_t vn = pos + 32 < start_limit ? load32u(src + pos + 32) : 0u;  // next window, in flight during this step
+        const uint32_t h = (v * 0x9E3779B1u) >> (32 - ENC_HBITS);
+        uint32_t slot = 0;
+        if (valid) slot = table[h];
         __syncwarp();
         const uint32_t grp = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-        if (valid && lane == 31 - __clz(grp)) table[h] = pos;  // highest position of the bucket wins
+        if (valid && lane == 31 - __clz(grp)) table[h] = (enc_slot_t)pos;  // highest position of the bucket wins
         __syncwarp();
-        const bool ok = valid && cand != ENC_EMPTY && pos - cand <= ENC_MAXOFF && load32u(src + cand) == v;
-        uint32_t mm = __ballot_sync(FULL, ok);
-        if (anchor > p) mm &= anchor - p >= 32 ? 0u : ~((1u << (anchor - p)) - 1);  // lanes covered by the previous match
-        while (mm) {
-            const int i = __ffs(mm) - 1;
-            const uint32_t mpos = p + i;
-            const uint32_t c = __shfl_sync(FULL, cand, i);
-            uint32_t len = 4;  // extend the match, 32 bytes per ballot
-            const uint32_t maxlen = match_limit - mpos;
-            for (;;) {
-                const uint32_t k = len + lane;
-                const bool eq = k < maxlen && __ldg(src + c + k) == __ldg(src + mpos + k);
-                const uint32_t ne = __ballot_sync(FULL, !eq);
-                if (ne) { len += __ffs(ne) - 1; break; }
-                len += 32;
+        const uint32_t d = (pos - slot) & 0xFFFFu;
+        const uint32_t cand = pos - d;
+        const bool probe = valid && d != 0 && d <= pos;
+        // position-side words at +4 and +8 (real only while pos + 8 < start_limit)
+        const uint32_t v4a = __shfl_sync(FULL, v, (lane + 4) & 31), v4b = __shfl_sync(FULL, vn, (lane + 4) & 31);
+        const uint32_t v8a = __shfl_sync(FULL, v, (lane + 8) & 31), v8b = __shfl_sync(FULL, vn, (lane + 8) & 31);
+        const uint32_t v4 = lane + 4 < 32 ? v4a : v4b, v8 = lane + 8 < 32 ? v8a : v8b;
+        uint32_t mlen = 0;  // this lane's match length: 0 none, 4..11 final, 12 = at least 12 (or not extended: see deep)
+        const bool deep = pos + 8 < start_limit;  // all 12 bytes on both sides are inside the input
+        if (probe) {
+            const uint32_t a = (uint32_t)((uintptr_t)(src + cand) & 3u);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(src + cand - a);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);  // w1 holds cand + 3 or lies inside [cand, pos): always in bounds
+            const uint32_t c0 = __funnelshift_r(w0, w1, a * 8);
+            if (deep) {
+                const uint32_t w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+                const uint32_t x1 = __funnelshift_r(w1, w2, a * 8) ^ v4, x2 = __funnelshift_r(w2, w3, a * 8) ^ v8;
+                if (c0 == v) mlen = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : (x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12);
+            } else if (c0 == v) {
+                mlen = 4;
             }
-            emit(anchor, mpos - anchor, mpos - c, len);
-            anchor = mpos + len;
-            const uint32_t covered = anchor - p;  // lanes below this were swallowed by the match
-            mm = covered >= 32 ? 0u : mm & ~((1u << covered) - 1);
         }
-        p = max(p + 32, anchor);
+        uint32_t mm = __ballot_sync(FULL, mlen != 0);
+        if (anchor > p) mm &= anchor - p >= 32 ? 0u : ~((1u << (anchor - p)) - 1);  // lanes covered by the previous match
+        if (mm) {
+            // greedy choice in position order; only matches that may be longer than 12 touch memory
+            const uint32_t open_ended = __ballot_sync(FULL, mlen == 12 || (mlen != 0 && !deep));
+            uint32_t sel = 0, last_end = 0;
+            while (mm) {
+                const int i = __ffs(mm) - 1;
+                const uint32_t mpos = p + i;
+                uint32_t len = __shfl_sync(FULL, mlen, i);
+                if ((open_ended >> i) & 1) {  // extend the match, 32 bytes per ballot
+                    const uint32_t c = __shfl_sync(FULL, cand, i);
+                    const uint32_t maxlen = match_limit - mpos;
+                    for (;;) {
+                        const uint32_t k = len + lane;
+                        const bool eq = k < maxlen && __ldg(src + c + k) == __ldg(src + mpos + k);
+                        const uint32_t ne = __ballot_sync(FULL, !eq);
+                        if (ne) { len += __ffs(ne) - 1; break; }
+                        len += 32;
+                    }
+                    if (lane == i) mlen = len;
+                }
+                sel |= 1u << i;
+                last_end = mpos + len;
+                const uint32_t covered = last_end - p;  // lanes below this were swallowed by the match
+                mm = covered >= 32 ? 0u : mm & ~((1u << covered) - 1);
+            }
+            if (!em.window(src, p, v, anchor, sel, mlen, d)) {
+                uint32_t s = sel, a = anchor;
+                while (s) {
+                    const int i = __ffs(s) - 1;
+                    s &= s - 1;
+                    const uint32_t len = __shfl_sync(FULL, mlen, i), off = __shfl_sync(FULL, d, i);
+                    em.serial(a, p + i - a, off, len);
+                    a = p + i + len;
+                }
+            }
+            anchor = last_end;
+        }
+        const uint32_t pnext = max(p + 32, anchor);
+        if (pnext == p + 32) v = vn;
+        else v = pnext + lane < start_limit ? load32u(src + pnext + lane) : 0u;
+        p = pnext;
     }
     return anchor;
 }

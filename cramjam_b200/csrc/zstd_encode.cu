@@ -65,20 +65,34 @@ struct FseC {
     }
 };
 
+// Collects the sequences and literal bytes of a block (find_matches emitter; one match at a time).
+struct ZSeqEmitter {
+    const uint8_t* __restrict__ src;
+    uint32_t* seq;
+    uint8_t* lits;
+    uint32_t nseq, nlit;
+    int lane;
+    __device__ __forceinline__ bool window(const uint8_t*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) { return false; }
+    __device__ __forceinline__ void serial(uint32_t lit_at, uint32_t ll, uint32_t off, uint32_t ml) {
+        for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = __ldg(src + lit_at + i);
+        if (lane == 0) { seq[3 * nseq] = ll; seq[3 * nseq + 1] = ml; seq[3 * nseq + 2] = off; }
+        nlit += ll;
+        nseq++;
+    }
+};
+
 // Encodes one block src[b0, b1) into out (room for at least (b1-b0) + 16 bytes).  Returns the block content size
 // written at out, or 0 if the block should be stored raw.
-__device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint32_t b1, uint32_t* table, uint32_t* seq, uint8_t* lits, uint8_t* out,
+__device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint32_t b1, enc_slot_t* table, uint32_t* seq, uint8_t* lits, uint8_t* out,
                              int lane) {
     const uint32_t bsz = b1 - b0;
     uint32_t nseq = 0, nlit = 0;
     uint32_t anchor = b0;
     if (bsz >= 8) {
-        anchor = find_matches(src, b0, b1 - 3, b1, table, lane, [&](uint32_t lit_at, uint32_t ll, uint32_t off, uint32_t ml) {
-            for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = __ldg(src + lit_at + i);
-            if (lane == 0) { seq[3 * nseq] = ll; seq[3 * nseq + 1] = ml; seq[3 * nseq + 2] = off; }
-            nlit += ll;
-            nseq++;
-        });
+        ZSeqEmitter em{src, seq, lits, nseq, nlit, lane};
+        anchor = find_matches(src, b0, b1 - 3, b1, table, lane, em);
+        nseq = em.nseq;
+        nlit = em.nlit;
     }
     if (nseq == 0) return 0;
     const uint32_t tail = b1 - anchor;
@@ -139,7 +153,7 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
     return op + 3 < bsz ? op : 0;
 }
 
-__device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, uint32_t* table, uint8_t* scratch, int lane,
+__device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, enc_slot_t* table, uint8_t* scratch, int lane,
                             uint32_t* produced) {
     *produced = 0;
     const uint64_t bound = (uint64_t)n + 3ull * (n / ZE_BLOCK + 1) + 18;
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(Batch b, uns
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t* table = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * ENC_HSIZE;
+    enc_slot_t* table = reinterpret_cast<enc_slot_t*>(smem) + (size_t)warp * ENC_HSIZE;
     uint8_t* my_scratch = scratch + ((size_t)blockIdx.x * ZE_WARPS + warp) * ZE_SCRATCH;
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
@@ -265,7 +279,7 @@ static cudaError_t upload_tables() {
 }
 
 int zstd_enc_grid(int sm_count, uint32_t n) {
-    int grid = sm_count * 3;
+    int grid = sm_count * 6;  // 8 KiB of shared memory per warp (lz_match.cuh) and <= 80 registers: 24 warps per SM
     const int need = (int)((n + ZE_WARPS - 1) / ZE_WARPS);
     if (grid > need) grid = need;
     return grid < 1 ? 1 : grid;
@@ -274,7 +288,7 @@ int zstd_enc_grid(int sm_count, uint32_t n) {
 size_t zstd_enc_scratch_bytes(int sm_count, uint32_t n) { return (size_t)zstd_enc_grid(sm_count, n) * ZE_WARPS * ZE_SCRATCH; }
 
 cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, cudaStream_t stream) {
-    const size_t smem = (size_t)ENC_HSIZE * 4 * ZE_WARPS;
+    const size_t smem = ENC_TABLE_BYTES * ZE_WARPS;
     static bool ready = false;
     if (!ready) {
         cudaError_t e = upload_tables();
