@@ -145,7 +145,18 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     unsigned* counters = c->counters + (slot & 63);
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream, reset_counter);
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
+            // Large batches outside the pinned pipeline take the two-kernel generation-3 path (lz_decode3.cu);
+            // CJ_DECODE_GEN=2 keeps everything on the one-warp-per-block kernel, CJ_G3_MIN_UNITS moves the threshold.
+            static const int gen = [] { const char* v = getenv("CJ_DECODE_GEN"); return v ? atoi(v) : 2; }();
+            static const long g3_min = [] { const char* v = getenv("CJ_G3_MIN_UNITS"); return v ? atol(v) : 4096L; }();
+            if (gen >= 3 && reset_counter && (long)b.n >= g3_min) {
+                e = cj::launch_lz_decode3(codec, b, c->g3, c->sm_count, c->stream);
+                c->launches += 3;
+            } else {
+                e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream, reset_counter);
+            }
+        }
         else if (codec == CJ_LZ4_FRAME) e = cj::launch_lz4f_decode(b, counters, c->sm_count, c->stream);
         else if (codec == CJ_ZSTD) {
             int rc = c->z_lit.ensure(cj::zstd_scratch_bytes(c->sm_count, b.n));

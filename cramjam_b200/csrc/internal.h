@@ -70,6 +70,30 @@ struct Scratch {
     }
 };
 
+// Scratch of the generation-3 decode path (lz_decode3.cu): per-unit plan arrays + the descriptor arena.
+struct G3Scratch {
+    Scratch fixed_, arena_;
+    int ensure_fixed(size_t bytes) { return fixed_.ensure(bytes); }
+    int ensure_arena(size_t bytes) { return arena_.ensure(bytes); }
+    void* fixed() const { return fixed_.p; }
+    void* arena() const { return arena_.p; }
+};
+// Optional view of the index kernel's output (tests / tools): device pointers, valid until the next call on the context.
+struct G3Debug {
+    bool index_only = false;
+    const uint32_t* desc_off = nullptr;
+    const uint32_t* count = nullptr;
+    const uint32_t* ulen = nullptr;
+    const uint32_t* desc = nullptr;
+    const uint32_t* rowbase = nullptr;
+    const unsigned* redo_count = nullptr;
+    unsigned long long total = 0;
+};
+namespace cj {
+// Two-kernel decode (index walk + lane state machines) for large batches; synchronises the stream once (plan read-back).
+cudaError_t launch_lz_decode3(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream, G3Debug* dbg = nullptr);
+}
+
 struct cj_ctx {
     int device = 0;
     int sm_count = 0;
@@ -86,12 +110,13 @@ struct cj_ctx {
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)
     Scratch z_lit, z_enc;                                              // zstd per-warp literal buffers / encoder scratch (device)
+    G3Scratch g3;                                                      // generation-3 LZ decode: plan arrays + descriptor arena (device)
     cj_ctx() {
         h_src.pinned = h_dst.pinned = h_desc.pinned = true;
         f_hsrc.pinned = f_hdst.pinned = f_hdesc.pinned = true;
     }
     void release_all() {
-        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc};
+        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc, &g3.fixed_, &g3.arena_};
         for (Scratch* s : all) s->release();
     }
 };

@@ -29,6 +29,7 @@ def parse_snappy(cs):
             els.append((False, 1 + (t >> 2), int.from_bytes(cs[ip:ip + 4], "little"))); ip += 4
     return els
 
+if __name__ != "__main__": sys.argv = sys.argv[:1]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 data = capi.synth_host(64, 65536)
 stats = {"prefix": [0, 0, 0], "precise": [0, 0, 0]}  # rounds, calls(32-job groups), jobs
