@@ -68,6 +68,8 @@ int cj_ctx_create(int device, cj_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("CJ_DECODE_GEN")) c->decode_gen = atoi(v);
+    if (const char* v = getenv("CJ_G3_MIN_UNITS")) c->g3_min_units = atol(v);
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUDA_TRY(cudaMalloc(&c->counters, 64 * sizeof(unsigned)));
@@ -111,6 +113,14 @@ int cj_ctx_synchronize(cj_ctx* c) {
 
 uint64_t cj_ctx_launch_count(const cj_ctx* c) { return c ? c->launches : 0; }
 
+int cj_ctx_set_decode_path(cj_ctx* c, int generation, long min_units) {
+    if (!c || (generation != 2 && generation != 3) || min_units < 1) return CJ_E_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    c->decode_gen = generation;
+    c->g3_min_units = min_units;
+    return CJ_OK;
+}
+
 int cj_ctx_last_kernel_ms(cj_ctx* c, float* ms) {
     if (!c || !ms) return CJ_E_INVALID_ARG;
     if (!c->ev_valid) {
@@ -146,11 +156,8 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
-            // Large batches outside the pinned pipeline take the two-kernel generation-3 path (lz_decode3.cu);
-            // CJ_DECODE_GEN=2 keeps everything on the one-warp-per-block kernel, CJ_G3_MIN_UNITS moves the threshold.
-            static const int gen = [] { const char* v = getenv("CJ_DECODE_GEN"); return v ? atoi(v) : 2; }();
-            static const long g3_min = [] { const char* v = getenv("CJ_G3_MIN_UNITS"); return v ? atol(v) : 4096L; }();
-            if (gen >= 3 && reset_counter && (long)b.n >= g3_min) {
+            // Generation 3 (lz_decode3.cu) is opt-in: cj_ctx_set_decode_path() or CJ_DECODE_GEN=3; see DESIGN.md §4.6 for why it is not the default.
+            if (c->decode_gen >= 3 && reset_counter && (long)b.n >= c->g3_min_units) {
                 e = cj::launch_lz_decode3(codec, b, c->g3, c->sm_count, c->stream);
                 c->launches += 3;
             } else {

@@ -106,6 +106,8 @@ struct cj_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
+    int decode_gen = 2;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu)
+    long g3_min_units = 4096;      // smallest batch the generation-3 path takes
     std::mutex mu;
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)

@@ -106,6 +106,7 @@ constexpr int IX_WARPS = 4;
 constexpr int IX_RING = 256;     // per-lane input ring (two 128-byte chunks)
 constexpr int IX_STRIDE = 33;    // staging row stride in words (bank-conflict free both ways)
 constexpr int IX_SMEM_WARP = 32 * IX_RING + 32 * IX_STRIDE * 4;
+constexpr int IX_SMEM_CTA = IX_SMEM_WARP * IX_WARPS + 1024;  // + the 256-entry tag table
 constexpr uint32_t IX_DELAY = 8;  // a chunk is read no earlier than this many iterations after its cp.async
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
@@ -115,6 +116,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Snappy tag table: [6:0] compressed size of the element, [14:8] bytes it produces, [23:16] descriptor top byte
+// (kind << 6 | f), bit 31 = not a plain element (literal with length bytes, 4-byte-offset copy).
+__device__ __forceinline__ uint32_t snappy_tag_entry(uint32_t tag) {
+    const uint32_t type = tag & 3, L = (tag >> 2) + 1;
+    if (type == 0) return L <= 60 ? ((1 + L) | (L << 8) | (((K_LIT << 6) | (L - 1)) << 16)) : 0x80000000u;
+    if (type == 1) {
+        const uint32_t len = 4 + ((tag >> 2) & 7);
+        return 2 | (len << 8) | (((K_M1 << 6) | ((len - 4) << 3) | (tag >> 5)) << 16);
+    }
+    if (type == 2) return 3 | (L << 8) | (((K_M16 << 6) | (L - 1)) << 16);
+    return 0x80000000u;
+}
+
 template <int CODEC>
 __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 g) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -123,34 +137,28 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
     uint8_t* wsm = smem + (size_t)warp * IX_SMEM_WARP;
     const uint32_t ring0 = smem_addr(wsm);
     const uint32_t ring = ring0 + lane * IX_RING;
-    const uint32_t stage = smem_addr(wsm + 32 * IX_RING);
-    const uint32_t nthreads = gridDim.x * blockDim.x;
-    uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stage0 = smem_addr(wsm + 32 * IX_RING);
+    const uint32_t stage = stage0 + lane * IX_STRIDE * 4;
+    const uint32_t lut = smem_addr(smem + (size_t)IX_SMEM_WARP * IX_WARPS);
+    if (CODEC == CJ_SNAPPY_RAW) {
+        for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(lut + 4 * t, snappy_tag_entry(t));
+        __syncthreads();
+    }
+    const uint32_t nwarps = gridDim.x * IX_WARPS;
 
-    bool active = false;
-    const uint8_t* src = nullptr;
-    uint32_t n = 0, ip = 0, op = 0, ulen = 0, e = 0, ecap = 0, doff = 0, cur = 0;
-    uint32_t loaded = 0, ready_old = 0, ready_new = 0, row_ip = 0, row_op = 0;
-    uint32_t litrem = 0;   // bytes of a long literal still to be described
-    uint32_t mrem = 0, mip = 0;  // LZ4: bytes of the current match still to be described, position of its offset
-    uint32_t lz_ll = 0;    // LZ4: literal bytes of the current sequence still to be described
-    bool lz_last = false;  // LZ4: the current sequence is the final, literal-only one
-    uint32_t nextp = 0;    // LZ4: where the walk continues once the current sequence is described
-    uint32_t iter = 0;
-
-    for (;;) {
-        // ---- (A) lanes without a block take the next one ----
-        if (!active && blk < b.n) {
-            cur = blk;
-            blk += nthreads;
+    for (uint32_t first = (blockIdx.x * IX_WARPS + warp) * 32; first < b.n; first += nwarps * 32) {
+        // ---- every lane takes one block ----
+        const uint32_t cur = first + lane;
+        bool active = false;
+        const uint8_t* src = nullptr;
+        uint32_t n = 0, ip = 0, op = 0, ulen = 0, e = 0, doff = 0;
+        if (cur < b.n) {
             doff = g.desc_off[cur];
-            ecap = g.desc_off[cur + 1] - doff;
-            if (ecap != 0) {  // else: the plan already sent it to generation 2
-                const uint64_t slen = b.src_len[cur], dcap = b.dst_cap[cur];
+            if (g.desc_off[cur + 1] != doff) {  // else: the plan already sent it to generation 2
+                const uint64_t dcap = b.dst_cap[cur];
                 src = b.src_base + b.src_off[cur];
-                n = (uint32_t)slen;
-                bool ok = true;
-                ip = 0;
+                n = (uint32_t)b.src_len[cur];
+                bool ok;
                 if (CODEC == CJ_SNAPPY_RAW) {
                     uint64_t v = 0;
                     bool done = false;
@@ -165,191 +173,188 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
                     ulen = (uint32_t)dcap;  // capacity: LZ4_decompress_safe's rules are applied against it
                     ok = dcap != 0;
                 }
-                if (ok) {
-                    active = true;
-                    op = 0; e = 0; litrem = 0; mrem = 0; lz_ll = 0; lz_last = false; nextp = 0;
-                    loaded = 0; ready_old = ready_new = iter + IX_DELAY;
-                } else {
-                    g3_redo(g, cur);
-                }
+                if (ok) active = true;
+                else g3_redo(g, cur);
             }
         }
-        if (!__any_sync(FULL, active || blk < b.n)) break;
+        const uint32_t n16 = n & ~15u;   // the ragged last granule is read straight from global memory
+        uint32_t loaded = 0, ready_old = IX_DELAY, ready_new = IX_DELAY, row_ip = 0, row_op = 0;
+        uint32_t litrem = 0;   // bytes of a long literal / LZ4 literal run still to be described (input position = ip)
+        uint32_t mrem = 0, mip = 0, nextp = 0;  // LZ4: match bytes still to be described, position of its offset, next token
+        bool lz_last = false;
+        uint32_t iter = 0;
 
-        // ---- (B) input ring: issue the next 128-byte chunk of every lane that has entered its newest one ----
-        const bool reading = active && litrem == 0 && mrem == 0 && lz_ll == 0 && !lz_last && ip < n;
-        const bool want = reading && ip + 128 >= loaded;
-        if (want && ip >= loaded) loaded = ip & ~127u;  // first chunk of the block, or a jump over a long literal
-        uint32_t wm = __ballot_sync(FULL, want);
-        while (wm) {
-            const int j = __ffs(wm) - 1;
-            wm &= wm - 1;
-            const uint32_t gl = __shfl_sync(FULL, loaded, j), nj = __shfl_sync(FULL, n, j);
-            const uint8_t* sp = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL, (unsigned long long)src, j));
-            if (lane < 8) {
-                const uint32_t go = gl + 16 * lane;
-                const uint32_t sa = ring0 + j * IX_RING + (go & (IX_RING - 1));
-                if (go + 16 <= nj) cp_async16(sa, sp + go);
-                else if (go < nj) {
-                    for (uint32_t t = 0; t < 16 && go + t < nj; t++) sts8(sa + t, ldg_u8(sp + go + t));
-                }
+        while (__any_sync(FULL, active)) {
+            // ---- input ring: issue the next 128-byte chunk of every lane that has entered its newest one ----
+            const bool reading = active && litrem == 0 && mrem == 0 && ip < n;
+            const bool want = reading && ip + 128 >= loaded;
+            if (want && ip >= loaded) loaded = ip & ~127u;  // first chunk of the block, or a jump over a long literal
+            uint32_t wm = __ballot_sync(FULL, want);
+            while (wm) {
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                const uint32_t go = __shfl_sync(FULL, loaded, j) + 16 * lane, nj = __shfl_sync(FULL, n16, j);
+                const uint8_t* sp = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL, (unsigned long long)src, j));
+                if (lane < 8 && go < nj) cp_async16(ring0 + j * IX_RING + (go & (IX_RING - 1)), sp + go);
             }
-        }
-        if (want) {
-            loaded += 128;
-            ready_old = ready_new;
-            ready_new = iter + IX_DELAY;
-        }
-        const bool can_read = reading && ((ip + 8 + 128 <= loaded && iter >= ready_old) || (ip + 8 <= loaded && iter >= ready_new));
+            if (want) {
+                loaded += 128;
+                ready_old = ready_new;
+                ready_new = iter + IX_DELAY;
+            }
+            const uint32_t limit = iter >= ready_new ? loaded : loaded - 128;
+            const bool can_read = reading && iter >= ready_old && ip + 8 <= limit;
 
-        // ---- (C) one step: at most one descriptor per lane ----
-        uint32_t d = 0, ipd = 0, opd = op;
-        bool emit = false, fin = false, fail = false;
-        if (active) {
+            uint32_t dtop = 0, ipd = ip, opd = op;
+            bool emit = false, fin = false, fail = false;
             if (CODEC == CJ_SNAPPY_RAW) {
-                if (litrem) {
-                    const uint32_t len = min(litrem, 60u);
-                    d = mk_desc(K_LIT, len - 1); ipd = ip; emit = true;
-                    ip += len; op += len; litrem -= len;
-                } else if (ip >= n) {
-                    fin = true;
-                    fail = op != ulen;
-                } else if (can_read) {
-                    const uint32_t tag = lds8(ring + (ip & (IX_RING - 1)));
-                    const uint32_t type = tag & 3, L = (tag >> 2) + 1;
-                    if (type == 0) {
-                        if (L <= 60) {
-                            if (L > n - ip - 1 || L > ulen - op) fail = true;   // ip < n here
-                            else { d = mk_desc(K_LIT, L - 1); ipd = ip + 1; emit = true; ip += 1 + L; op += L; }
-                        } else {
-                            const uint32_t nb = L - 60;
-                            if (nb > n - ip - 1) fail = true;
-                            else {
-                                uint32_t v = 0;
-                                for (uint32_t i = 0; i < nb; i++) v |= lds8(ring + ((ip + 1 + i) & (IX_RING - 1))) << (8 * i);
-                                const uint64_t LL = (uint64_t)v + 1;
-                                ip += 1 + nb;
-                                if (LL > n - ip || LL > ulen - op) fail = true;
-                                else litrem = (uint32_t)LL;
-                            }
+                // ---- hot path: one plain element per lane, table-driven ----
+                uint32_t ent = 0x80000000u;
+                if (can_read) {
+                    const uint32_t tag = ip < n16 ? lds8(ring + (ip & (IX_RING - 1))) : ldg_u8(src + ip);
+                    ent = lds32(lut + 4 * tag);
+                    if (!(ent >> 31)) {
+                        const uint32_t adv = ent & 0x7F, len = (ent >> 8) & 0x7F;
+                        if (adv > n - ip || len > ulen - op) fail = true;
+                        else {
+                            dtop = (ent << 8) & 0xFF000000u; ipd = ip + 1; emit = true;
+                            ip += adv; op += len;
                         }
-                    } else if (type == 1) {
-                        const uint32_t len = 4 + ((tag >> 2) & 7);
-                        if (n - ip < 2 || len > ulen - op) fail = true;
-                        else { d = mk_desc(K_M1, ((len - 4) << 3) | (tag >> 5)); ipd = ip + 1; emit = true; ip += 2; op += len; }
-                    } else if (type == 2) {
-                        if (n - ip < 3 || L > ulen - op) fail = true;
-                        else { d = mk_desc(K_M16, L - 1); ipd = ip + 1; emit = true; ip += 3; op += L; }
-                    } else {
-                        fail = true;  // 4-byte offsets: generation 2
+                    }
+                }
+                if (active && !emit && !fail) {  // rare states
+                    if (litrem) {
+                        const uint32_t len = min(litrem, 60u);
+                        dtop = mk_desc(K_LIT, len - 1); emit = true;
+                        ip += len; op += len; litrem -= len;
+                    } else if (ip >= n) {
+                        fin = true;
+                        fail = op != ulen;
+                    } else if (can_read) {
+                        const uint32_t tag = ip < n16 ? lds8(ring + (ip & (IX_RING - 1))) : ldg_u8(src + ip);
+                        const uint32_t nb = (tag >> 2) + 1 - 60;
+                        if ((tag & 3) != 0 || nb > n - ip - 1) fail = true;   // 4-byte-offset copies: generation 2
+                        else {
+                            uint32_t v = 0;
+                            for (uint32_t i = 0; i < nb; i++) {
+                                const uint32_t p = ip + 1 + i;
+                                v |= (p < n16 ? lds8(ring + (p & (IX_RING - 1))) : ldg_u8(src + p)) << (8 * i);
+                            }
+                            const uint64_t LL = (uint64_t)v + 1;
+                            ip += 1 + nb;
+                            if (LL > n - ip || LL > ulen - op) fail = true;
+                            else litrem = (uint32_t)LL;
+                        }
                     }
                 }
             } else {
                 // LZ4: a sequence is described as literal chunks (<= 64 B) followed by match chunks (<= 64 B).
                 // The checks are lz4_serial_step's (lz_decode.cuh); whatever they would reject goes to generation 2.
-                if (lz_ll) {
-                    const uint32_t len = min(lz_ll, 64u);
-                    d = mk_desc(K_LIT, len - 1); ipd = ip; emit = true;
-                    ip += len; op += len; lz_ll -= len;
-                    if (lz_ll == 0 && lz_last) fin = true;
-                } else if (mrem) {
-                    const uint32_t len = min(mrem, 64u);
-                    d = mk_desc(K_M16, len - 1); ipd = mip; emit = true;
-                    op += len; mrem -= len;
-                } else if (ip >= n) {
-                    fail = true;  // a valid block ends inside a literal-only sequence
-                } else if (can_read) {
-                    const uint32_t token = lds8(ring + (ip & (IX_RING - 1)));
-                    uint32_t q = ip + 1, ll = token >> 4, ml = token & 15;
-                    bool irregular = false;
-                    if (ll == 15) {
-                        if (n < 15 || q >= n - 15) irregular = true;
-                        else {
-                            uint32_t x = 255, cnt = 0;
-                            while (x == 255 && cnt < 4) {   // the ring guarantees ip + 8 bytes; longer runs: generation 2
-                                x = lds8(ring + (q & (IX_RING - 1)));
-                                q++; ll += x; cnt++;
-                                if (q > n - 15) { irregular = true; break; }
+                if (active) {
+                    if (litrem == 0 && mrem == 0 && !lz_last) {
+                        if (ip >= n) fail = true;  // a valid block ends inside a literal-only sequence
+                        else if (can_read) {
+                            auto rb = [&](uint32_t p) -> uint32_t { return p < n16 ? lds8(ring + (p & (IX_RING - 1))) : ldg_u8(src + p); };
+                            const uint32_t token = rb(ip);
+                            uint32_t q = ip + 1, ll = token >> 4, ml = token & 15;
+                            bool irregular = false;
+                            if (ll == 15) {
+                                if (n < 15 || q >= n - 15) irregular = true;
+                                else {
+                                    uint32_t x = 255, cnt = 0;
+                                    while (x == 255 && cnt < 4) {   // the ring guarantees ip + 8 bytes; longer runs: generation 2
+                                        x = rb(q);
+                                        q++; ll += x; cnt++;
+                                        if (q > n - 15) { irregular = true; break; }
+                                    }
+                                    irregular = irregular || x == 255;
+                                }
                             }
-                            irregular = irregular || x == 255;
+                            if (irregular) fail = true;
+                            else if ((uint64_t)op + ll + 12 > ulen || (uint64_t)q + ll + 8 > n) {
+                                // tail zone: must be the final literal-only sequence, ending exactly at n
+                                if ((uint64_t)q + ll != n || (uint64_t)op + ll > ulen) fail = true;
+                                else { ip = q; lz_last = true; litrem = ll; }
+                            } else {
+                                // regular sequence (at least 6 bytes follow the offset); the match-length bytes sit behind the
+                                // literals, possibly outside the ring window: read from global memory (L1/L2)
+                                const uint32_t po = q + ll;
+                                uint32_t r = po + 2;
+                                if (ml == 15) {
+                                    uint32_t x = 255, cnt = 0;
+                                    while (x == 255 && cnt < 16) {
+                                        x = ldg_u8(src + r);
+                                        r++; ml += x; cnt++;
+                                        if (r > n - 4) { irregular = true; break; }
+                                    }
+                                    irregular = irregular || x == 255;
+                                }
+                                ml += 4;
+                                if (irregular || (uint64_t)op + ll + ml + 5 > ulen) fail = true;
+                                else { ip = q; litrem = ll; mip = po; mrem = ml; nextp = r; }
+                            }
                         }
                     }
-                    if (irregular) fail = true;
-                    else if ((uint64_t)op + ll + 12 > ulen || (uint64_t)q + ll + 8 > n) {
-                        // tail zone: must be the final literal-only sequence, ending exactly at n
-                        if ((uint64_t)q + ll != n || (uint64_t)op + ll > ulen) fail = true;
-                        else {
-                            ip = q;
-                            lz_last = true;
-                            if (ll == 0) fin = true;
-                            else lz_ll = ll;
+                    if (!fail) {  // describe one chunk of the current sequence (also in the iteration that parsed it)
+                        if (litrem) {
+                            const uint32_t len = min(litrem, 64u);
+                            dtop = mk_desc(K_LIT, len - 1); ipd = ip; opd = op; emit = true;
+                            ip += len; op += len; litrem -= len;
+                        } else if (mrem) {
+                            const uint32_t len = min(mrem, 64u);
+                            dtop = mk_desc(K_M16, len - 1); ipd = mip; opd = op; emit = true;
+                            op += len; mrem -= len;
+                            if (mrem == 0) ip = nextp;
                         }
-                    } else {
-                        // regular sequence (at least 6 bytes follow the offset).  Offset and match-length bytes sit behind the
-                        // literals, possibly outside the ring window: the length bytes are read from global memory (L1/L2).
-                        const uint32_t po = q + ll;
-                        uint32_t r = po + 2;
-                        if (ml == 15) {
-                            uint32_t x = 255, cnt = 0;
-                            while (x == 255 && cnt < 16) {
-                                x = ldg_u8(src + r);
-                                r++; ml += x; cnt++;
-                                if (r > n - 4) { irregular = true; break; }
-                            }
-                            irregular = irregular || x == 255;
-                        }
-                        ml += 4;
-                        if (irregular || (uint64_t)op + ll + ml + 5 > ulen) fail = true;
-                        else { ip = q; lz_ll = ll; mip = po; mrem = ml; nextp = r; }
+                        if (lz_last && litrem == 0) fin = true;
                     }
                 }
-                // after the last chunk of a regular sequence the walk continues behind its match-length bytes
-                if (nextp && lz_ll == 0 && mrem == 0) { ip = nextp; nextp = 0; }
             }
-        }
-        if (emit) {
-            const uint32_t k = e & 31;
-            if (k == 0) {
-                row_ip = ipd; row_op = opd;
-                if (e < ecap) g.rowbase[(doff + e) >> 5] = make_uint2(ipd, opd);
+            if (emit) {
+                const uint32_t k = e & 31;
+                if (k == 0) {
+                    row_ip = ipd; row_op = opd;
+                    g.rowbase[(doff + e) >> 5] = make_uint2(ipd, opd);
+                }
+                const uint32_t dip = ipd - row_ip, dop = opd - row_op;
+                if (CODEC != CJ_SNAPPY_RAW && (dip > 4095 || dop > 4095)) fail = true;  // Snappy: <= 31 x 65 by construction
+                else {
+                    sts32(stage + k * 4, dtop | (dip << 12) | dop);
+                    e++;
+                }
             }
-            const uint32_t dip = ipd - row_ip, dop = opd - row_op;
-            if (dip > 4095 || dop > 4095 || e >= ecap) fail = true;
-            else {
-                sts32(stage + (lane * IX_STRIDE + k) * 4, d | (dip << 12) | dop);
-                e++;
+            if (fail) {
+                g3_redo(g, cur);
+                active = false;
+                fin = false;
             }
-        }
-        if (fail) {
-            g3_redo(g, cur);
-            active = false;
-            fin = false;
-        }
-        // ---- (D) rows leave the staging area: full rows, and the partial last row of a finished block ----
-        const bool flushrow = active && ((emit && (e & 31) == 0) || (fin && (e & 31) != 0));
-        const uint32_t rcount = (e & 31) ? (e & 31) : 32;
-        const uint32_t rstart = doff + ((e - 1) & ~31u);
-        uint32_t fm = __ballot_sync(FULL, flushrow);
-        if (fm) {
+            // ---- rows leave the staging area: full rows, and the partial last row of a finished block ----
+            const bool flushrow = active && ((emit && (e & 31) == 0) || (fin && (e & 31) != 0));
+            uint32_t fm = __ballot_sync(FULL, flushrow);
+            if (fm) {
+                const uint32_t rcount = (e & 31) ? (e & 31) : 32;
+                const uint32_t rstart = doff + ((e - 1) & ~31u);
+                __syncwarp();
+                while (fm) {
+                    const int j = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const uint32_t rs = __shfl_sync(FULL, rstart, j), rc = __shfl_sync(FULL, rcount, j);
+                    if ((uint32_t)lane < rc) g.desc[rs + lane] = lds32(stage0 + (j * IX_STRIDE + lane) * 4);
+                }
+            }
+            if (fin) {  // fail cleared fin
+                g.count[cur] = e;
+                g.ulen[cur] = (CODEC == CJ_SNAPPY_RAW) ? ulen : op;
+                active = false;
+            }
+            cp_async_commit();
+            cp_async_wait<IX_DELAY - 1>();
             __syncwarp();
-            while (fm) {
-                const int j = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const uint32_t rs = __shfl_sync(FULL, rstart, j), rc = __shfl_sync(FULL, rcount, j);
-                if ((uint32_t)lane < rc) g.desc[rs + lane] = lds32(stage + (j * IX_STRIDE + lane) * 4);
-            }
+            iter++;
         }
-        if (fin && active) {
-            g.count[cur] = e;
-            g.ulen[cur] = (CODEC == CJ_SNAPPY_RAW) ? ulen : op;
-            active = false;
-        }
-        cp_async_commit();
-        cp_async_wait<IX_DELAY - 1>();
+        cp_async_wait<0>();
         __syncwarp();
-        iter++;
     }
-    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,47 +525,73 @@ __global__ void __launch_bounds__(X_WARPS * 32, CJ_G3_CTAS) g3_exec_kernel(Batch
             }
             if (__any_sync(FULL, bad)) break;
 
-            // ---- move up to CH bytes of the lane's element ----
+            // ---- move up to CH bytes of the lane's element (word-wise: bytes travel packed in 32-bit registers) ----
             if (rem) {
+                constexpr int NW = CH / 4;
                 const uint32_t di = (dpos + out.a) & X_OMASK;
                 uint32_t c = min(min((uint32_t)CH, rem), X_OR - di);
-                uint32_t v[CH];
+                uint32_t w[NW];
                 bool ready = true;
                 if (is_lit) {
                     const uint32_t si = (sp + in.a) & IMASK;
                     c = min(c, (uint32_t)IRING - si);
-                    const uint32_t sa = in.ring + si;
+                    const uint32_t sa = in.ring + si, al = sa & ~3u, sh = (sa & 3u) * 8;
+                    uint32_t x[NW + 1];
 #pragma unroll
-                    for (int k = 0; k < CH; k++) v[k] = (uint32_t)k < c ? lds8(sa + k) : 0u;
+                    for (int k = 0; k <= NW; k++) x[k] = lds32(al + 4 * k);  // reads past si + c stay inside this warp's shared memory
+#pragma unroll
+                    for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(x[k], x[k + 1], sh);
                 } else {
                     const uint32_t s = dpos - sp;
                     c = min(c, sp);
                     const uint32_t si = (s + out.a) & X_OMASK;
                     c = min(c, X_OR - si);
-                    const uint32_t sa = oring + 2 * si;
-                    const uint32_t gs = ((s + out.a) >> X_LOG_OR) & 0xFF;
-                    bool hit = true;
+                    const uint32_t ea = oring + 2 * si, al = ea & ~7u, sh = (ea & 7u) * 8;  // sh in {0,16,32,48}
+                    uint32_t q[2 * NW + 2];
 #pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        v[k] = (uint32_t)k < c ? lds16(sa + 2 * k) : (gs << 8);
-                        hit = hit && (v[k] >> 8) == gs;
+                    for (int k = 0; k < NW + 1; k++) {
+                        uint32_t lo, hi;
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(al + 8 * k));
+                        q[2 * k] = lo; q[2 * k + 1] = hi;
                     }
-                    if (!hit) {
+                    const bool up = (sh & 32u) != 0;
+                    const uint32_t s5 = sh & 31u;
+                    const uint32_t E = (((s + out.a) >> X_LOG_OR) & 0xFF) * 0x01000100u;   // expected generation in both tag bytes
+                    uint32_t miss = 0;
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const uint32_t b0 = up ? q[2 * k + 1] : q[2 * k];
+                        const uint32_t b1 = up ? q[2 * k + 2] : q[2 * k + 1];
+                        const uint32_t b2 = up ? q[2 * k + 3] : q[2 * k + 2];
+                        const uint32_t e01 = __funnelshift_r(b0, b1, s5), e23 = __funnelshift_r(b1, b2, s5);
+                        const uint32_t cc = c > (uint32_t)(4 * k) ? c - 4 * k : 0u;   // entries of this word that matter
+                        const uint32_t m01 = cc >= 2 ? 0xFF00FF00u : (cc == 1 ? 0x0000FF00u : 0u);
+                        const uint32_t m23 = cc >= 4 ? 0xFF00FF00u : (cc == 3 ? 0x0000FF00u : 0u);
+                        miss |= ((e01 ^ E) & m01) | ((e23 ^ E) & m23);
+                        w[k] = __byte_perm(e01, e23, 0x6420);
+                    }
+                    if (miss) {
                         if (s < out.flushed) {  // slot overwritten: the bytes were drained, re-read them from global memory
                             c = min(c, out.flushed - s);
+                            const uintptr_t p = (uintptr_t)(dst + s);
+                            const uint32_t* ap = reinterpret_cast<const uint32_t*>(p & ~(uintptr_t)3);
+                            const uint32_t gsh = ((uint32_t)p & 3u) * 8;
+                            uint32_t x[NW + 1];
 #pragma unroll
-                            for (int k = 0; k < CH; k++) v[k] = (uint32_t)k < c ? (uint32_t)dst[s + k] : 0u;
+                            for (int k = 0; k <= NW; k++) x[k] = ap[k];   // at most 7 bytes past s + c, still far below dpos
+#pragma unroll
+                            for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(x[k], x[k + 1], gsh);
                         } else {
                             ready = false;  // source not produced yet
                         }
                     }
                 }
                 if (ready) {
-                    const uint32_t gd = (((dpos + out.a) >> X_LOG_OR) & 0xFF) << 8;
+                    const uint32_t gd = ((dpos + out.a) >> X_LOG_OR) & 0xFF;
                     const uint32_t da = oring + 2 * di;
 #pragma unroll
                     for (int k = 0; k < CH; k++)
-                        if ((uint32_t)k < c) sts16(da + 2 * k, (v[k] & 0xFF) | gd);
+                        if ((uint32_t)k < c) sts16(da + 2 * k, __byte_perm(w[k / 4], gd, 0x0040 | (k & 3)));
                     dpos += c;
                     rem -= c;
                     if (is_lit) sp += c;
@@ -634,7 +665,7 @@ static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaSt
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e;
-        if ((e = set_smem(g3_index_kernel<CODEC>, (size_t)IX_SMEM_WARP * IX_WARPS)) != cudaSuccess) return e;
+        if ((e = set_smem(g3_index_kernel<CODEC>, (size_t)IX_SMEM_CTA)) != cudaSuccess) return e;
         if ((e = set_smem(g3_exec_kernel<CODEC>, (size_t)X_SMEM_WARP * X_WARPS)) != cudaSuccess) return e;
         if ((e = set_smem(lz_decode_list_kernel<CODEC>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
         attr_done = true;
@@ -666,7 +697,7 @@ static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaSt
     g.arena = total;
     if (total) {
         int grid = (int)std::min<size_t>((n + IX_WARPS * 32 - 1) / (IX_WARPS * 32), (size_t)sm_count * 4);
-        g3_index_kernel<CODEC><<<grid, IX_WARPS * 32, (size_t)IX_SMEM_WARP * IX_WARPS, stream>>>(b, g);
+        g3_index_kernel<CODEC><<<grid, IX_WARPS * 32, (size_t)IX_SMEM_CTA, stream>>>(b, g);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (!(dbg && dbg->index_only)) {
             grid = (int)std::min<size_t>((n + X_WARPS - 1) / X_WARPS, (size_t)sm_count * CJ_G3_CTAS);
