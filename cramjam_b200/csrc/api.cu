@@ -172,8 +172,15 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         }
         else { cj_set_error("codec %d has no device-resident batch decoder", codec); return CJ_E_INVALID_ARG; }
     } else {
-        int accel = params && params->acceleration > 0 ? params->acceleration : 1;
-        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, accel, c->stream, reset_counter);
+        // speed / ratio knob of the block encoders: lz4 `acceleration` > 1 shrinks the match table (faster, lower ratio),
+        // an HC-class level (lz4 block `compression=Some(n)`, lz4 frame level >= 3) grows it.  Snappy has no knob.
+        int effort = 2;
+        if (codec == CJ_LZ4_BLOCK && params) {
+            if (params->level >= 3) effort = 3;
+            else if (params->acceleration >= 4) effort = 0;
+            else if (params->acceleration >= 2) effort = 1;
+        }
+        if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) e = cj::launch_lz_encode(codec, b, counters, c->sm_count, effort, c->stream, reset_counter);
         else if (codec == CJ_ZSTD) {
             int rc = c->z_enc.ensure(cj::zstd_enc_scratch_bytes(c->sm_count, b.n));
             if (rc) return rc;

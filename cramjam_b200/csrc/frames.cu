@@ -614,7 +614,8 @@ int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
 
 // ---- LZ4 frame compress: independent 64 KiB blocks + content checksum --------------------------------
 int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* params) {
-    (void)params;  // every level maps to the greedy block encoder (LZ4HC-class levels are a "next" row)
+    // level >= 3 is LZ4HC in the reference (src/lz4.rs:17 default 4): the block encoder runs with its largest match table
+    cj_params blk{params ? params->level : 4, 1, 0};
     const size_t n = bt->n;
     std::vector<uint64_t> sbase;
     int rc;
@@ -652,7 +653,7 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         b.n = (uint32_t)nc;
         b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = dch.so; b.src_len = dch.sl;
         b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = dch.dof; b.dst_cap = dch.dc; b.dst_len = dch.dl; b.status = dch.st;
-        if ((rc = cj_run_device_batch(c, CJ_LZ4_BLOCK, true, b, nullptr))) return rc;
+        if ((rc = cj_run_device_batch(c, CJ_LZ4_BLOCK, true, b, &blk))) return rc;
     }
     if ((rc = launch_xxh32(c, (uint32_t)n, (const uint8_t*)c->f_dsrc.p, dwhole.so, dwhole.sl, dwhole.aux))) return rc;
     if ((rc = fetch_results(c, dch))) return rc;

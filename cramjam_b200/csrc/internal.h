@@ -27,7 +27,7 @@ void cj_set_error(const char* fmt, ...);
 
 namespace cj {
 cudaError_t launch_lz_decode(int codec, const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter = true);
-cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int acceleration, cudaStream_t stream, bool reset_counter = true);
+cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int sm_count, int effort, cudaStream_t stream, bool reset_counter = true);
 cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
 cudaError_t launch_zstd_decode(const Batch& b, unsigned* counter, uint8_t* lit_scratch, int sm_count, cudaStream_t stream);
 size_t zstd_scratch_bytes(int sm_count, uint32_t n);

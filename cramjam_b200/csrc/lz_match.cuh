@@ -9,7 +9,10 @@
 
 namespace cj {
 
-constexpr int ENC_HBITS = 12;
+#ifndef CJ_ENC_HBITS
+#define CJ_ENC_HBITS 12
+#endif
+constexpr int ENC_HBITS = CJ_ENC_HBITS;
 constexpr int ENC_HSIZE = 1 << ENC_HBITS;
 constexpr uint32_t ENC_MAXOFF = 65535;
 // A table slot keeps the low 16 bits of a position.  The candidate is rebuilt as pos - ((pos - slot) & 0xFFFF):
@@ -29,8 +32,9 @@ __device__ __forceinline__ uint32_t load32u(const uint8_t* p) {  // unaligned li
     return __funnelshift_r(lo, hi, a * 8);
 }
 
+template <int HBITS = ENC_HBITS>
 __device__ __forceinline__ void match_table_reset(enc_slot_t* table, int lane) {
-    for (uint32_t i = lane; i < ENC_TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = lane; i < ((size_t)sizeof(enc_slot_t) << HBITS) / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 }
 
@@ -48,7 +52,8 @@ __device__ __forceinline__ void match_table_reset(enc_slot_t* table, int lane) {
 //                                              src[p + lane]); anchor = start of the pending literal run.
 //                                              Returns false if it wants the step one match at a time instead:
 //   em.serial(anchor, literal_len, offset, match_len)  warp-uniform.
-template <class Emitter>
+// HBITS = log2 of the table size: the speed / ratio knob of the block encoders (lz4 `acceleration`, HC-class levels).
+template <class Emitter, int HBITS = ENC_HBITS>
 __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src, uint32_t begin, uint32_t start_limit, uint32_t match_limit,
                                                  enc_slot_t* table, int lane, Emitter& em) {
     uint32_t anchor = begin;
@@ -58,7 +63,7 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
         const uint32_t pos = p + lane;
         const bool valid = pos < start_limit;
         const uint32_t vn = pos + 32 < start_limit ? load32u(src + pos + 32) : 0u;  // next window, in flight during this step
-        const uint32_t h = (v * 0x9E3779B1u) >> (32 - ENC_HBITS);
+        const uint32_t h = (v * 0x9E3779B1u) >> (32 - HBITS);
         uint32_t slot = 0;
         if (valid) slot = table[h];
         __syncwarp();

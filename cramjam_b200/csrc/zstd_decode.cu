@@ -18,7 +18,13 @@
 
 namespace cj {
 
-constexpr int ZS_WARPS = 4;
+#ifndef CJ_ZS_WARPS
+#define CJ_ZS_WARPS 3
+#endif
+#ifndef CJ_ZS_CTAS
+#define CJ_ZS_CTAS 5
+#endif
+constexpr int ZS_WARPS = CJ_ZS_WARPS;   // 3 warps x 14.5 KiB: five CTAs (15 warps) fit an SM, four 4-warp CTAs would not
 constexpr uint32_t ZS_BLOCK_MAX = 128 * 1024;
 constexpr size_t ZS_LIT_STRIDE = ZS_BLOCK_MAX + 64;  // per-warp literal buffer in global scratch
 
@@ -662,7 +668,7 @@ __global__ void __launch_bounds__(ZS_WARPS * 32) zstd_decode_kernel(Batch b, uns
 }
 
 int zstd_grid(int sm_count, uint32_t n) {
-    int grid = sm_count * 3;  // 3 CTAs x 4 warps x 14.5 KiB of shared memory per SM
+    int grid = sm_count * CJ_ZS_CTAS;  // CTAs x warps x 14.5 KiB of shared memory per SM
     const int need = (int)((n + ZS_WARPS - 1) / ZS_WARPS);
     if (grid > need) grid = need;
     return grid < 1 ? 1 : grid;

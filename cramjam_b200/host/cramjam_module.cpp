@@ -370,8 +370,9 @@ static void add_stream_classes(M& m, cj_codec codec, int kind, int default_level
 }
 
 // ---- lz4 block helpers (src/lz4.rs:78-229) ----
-static std::vector<uint8_t> lz4_block_compress(const uint8_t* p, size_t n, bool store_size, int accel) {
-    std::vector<uint8_t> c = do_compress(CJ_LZ4_BLOCK, p, n, -1, accel);
+// `compression=Some(n)` is CompressionMode::HIGHCOMPRESSION(n) in the reference (src/lz4.rs:113-131): passed as the level
+static std::vector<uint8_t> lz4_block_compress(const uint8_t* p, size_t n, bool store_size, int accel, int compression = -1) {
+    std::vector<uint8_t> c = do_compress(CJ_LZ4_BLOCK, p, n, compression >= 0 ? std::max(compression, 3) : -1, accel);
     if (!store_size) return c;
     std::vector<uint8_t> out(c.size() + 4);
     const uint32_t sz = (uint32_t)n;  // 4-byte little-endian uncompressed-size prefix (lz4::block, prepend_size)
@@ -646,9 +647,10 @@ PYBIND11_MODULE(cramjam, m) {
               py::arg("input"), py::arg("output"), py::arg("level") = py::none());
         l.def("decompress_into", [](py::handle input, py::handle output) { return generic_decompress_into(CJ_LZ4_FRAME, input, output); }, py::arg("input"), py::arg("output"));
         // block API; `mode` and `output_len` of compress_block are accepted and ignored (src/lz4.rs:114,120)
-        l.def("compress_block", [](py::handle data, py::object, py::object, py::object acceleration, py::object, py::object store_size) {
+        l.def("compress_block", [](py::handle data, py::object, py::object, py::object acceleration, py::object compression, py::object store_size) {
             Input in(data);
-            return make_buffer(lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>()));
+            return make_buffer(lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>(),
+                                                  compression.is_none() ? -1 : compression.cast<int>()));
         }, py::arg("data"), py::arg("output_len") = py::none(), py::arg("mode") = py::none(), py::arg("acceleration") = py::none(),
               py::arg("compression") = py::none(), py::arg("store_size") = py::none());
         l.def("decompress_block", [](py::handle data, py::object output_len) {
@@ -692,10 +694,11 @@ PYBIND11_MODULE(cramjam, m) {
             if (written) std::memcpy(out.b.buf, tmp.data(), written);
             return written;
         }, py::arg("input"), py::arg("output"), py::arg("output_len") = py::none());
-        l.def("compress_block_into", [](py::handle data, py::handle output, py::object, py::object acceleration, py::object, py::object store_size) {
+        l.def("compress_block_into", [](py::handle data, py::handle output, py::object, py::object acceleration, py::object compression, py::object store_size) {
             Input in(data);
             PyBuf out(output);
-            std::vector<uint8_t> c = lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>());
+            std::vector<uint8_t> c = lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>(),
+                                                        compression.is_none() ? -1 : compression.cast<int>());
             if (c.size() > (size_t)out.b.len) raise(g_compression_error, "Compression failed: output buffer is too small");
             std::memcpy(out.b.buf, c.data(), c.size());
             return c.size();

@@ -82,3 +82,23 @@ def test_ratio_close_to_cpu_encoder_on_synthetic_blocks(codec, ocomp):
     odec = (lambda c: O.lz4_block_decompress(c, U)) if codec == capi.LZ4_BLOCK else O.snappy_raw_decompress
     for u, c in zip(units[::16], outs[::16]):
         assert odec(c) == u
+
+
+def test_lz4_effort_knobs_round_trip_and_order():
+    """lz4 `acceleration` (src/lz4.rs:113-131) shrinks the match table, an HC-class level grows it: every setting must
+    round-trip through the oracle and liblz4, and the compressed size must not grow with the effort."""
+    n, U = 96, 65536
+    data = capi.synth_host(n, U, seed=0xC0FFEE, first_index=40)
+    blocks = [data[i * U:(i + 1) * U].tobytes() for i in range(n)]
+    bound = capi.lib().cj_compress_bound(capi.LZ4_BLOCK, U)
+    sizes = []
+    for kw in (dict(acceleration=8), dict(acceleration=2), dict(), dict(level=9)):
+        enc, st = ctx().run_host_units(capi.LZ4_BLOCK, True, blocks, [bound] * n, **kw)
+        assert (st == 0).all()
+        for c, b in zip(enc[::7], blocks[::7]):
+            assert O.lz4_block_decompress(c, U) == b
+            if S.have_lz4:
+                assert S.lz4_decompress(c, U) == b
+        sizes.append(sum(len(c) for c in enc))
+    assert sizes[0] >= sizes[1] >= sizes[2] >= sizes[3], sizes
+    assert sizes[0] > sizes[3]
