@@ -426,7 +426,7 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     }
     std::lock_guard<std::mutex> g(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
-    if (codec == CJ_SNAPPY_FRAMED || (codec == CJ_LZ4_FRAME && compress))
+    if (codec == CJ_SNAPPY_FRAMED || (codec == CJ_LZ4_FRAME && (compress || where != CJ_DEVICE)))
         return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
     // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
     if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME && codec != CJ_ZSTD) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }

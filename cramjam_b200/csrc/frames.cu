@@ -11,6 +11,8 @@
 // device (linked blocks depend on the previous 64 KiB of output, so blocks of one frame run in
 // order); XXH32 header / block / content checksums are verified in the same kernel.  The encoders
 // emit independent 64 KiB blocks (legal LZ4F), one unit of the block encoder each.
+#include <chrono>
+
 #include "internal.h"
 #include "lz_decode.cuh"
 
@@ -82,13 +84,91 @@ __device__ uint32_t xxh32_global(const uint8_t* p, uint64_t n) {
     return xxh32_generic([&](uint64_t q) { return __ldcg(p + q); }, n, 0);
 }
 
-__global__ void xxh32_units_kernel(uint32_t n, const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
-                                   uint32_t* __restrict__ out) {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+// XXH32 of every unit, one warp per unit.  The four accumulators of XXH32 are four independent serial chains
+// (acc = rotl(acc + w * P2, 13) * P1 over every fourth word), so one unit cannot go faster than one chain step per
+// 16 bytes; what the warp adds is the memory side: all 32 lanes stream the unit in 512-byte rows (one coalesced
+// 16-byte load per lane, the next row in flight while the current one is hashed), rows are parked in shared memory
+// and lanes 0..3 run one accumulator each.  (The one-thread-per-unit loop this replaces exposed a full DRAM round
+// trip per 16 bytes: 5 s for a 256 MiB frame; this kernel is chain-bound at ~2 GB/s per unit.)
+// Warp-cooperative XXH32 of p[0, L) (p 16-byte aligned, L2-coherent loads); `rows` = 2 x 128 words of this warp's shared memory.
+// Every lane returns the hash.  Rows are stored transposed (the 32 words of accumulator i contiguous) so that lane i pulls its
+// words with eight 16-byte loads and runs its chain in registers.  The chain itself is folded to two dependent operations per
+// step: with s = acc + w*P2, rotl(s,13)*P1 = s*(P1<<13) + (s>>19)*P1 (the two halves of the rotation occupy disjoint bits),
+// so the next s is (s>>19)*P1 + (s*(P1<<13) + w'*P2) — a shift and a multiply-add side by side, then one multiply-add.
+__device__ __forceinline__ uint32_t xxh32_warp(const uint8_t* p, uint64_t L, uint32_t* rows, int lane) {
+    const uint64_t stripes = L / 16;           // 16-byte stripes the main loop consumes
+    const uint64_t nrows = (stripes + 31) / 32;
+    constexpr uint32_t K13 = XP1 << 13;
+    uint32_t acc = lane == 0 ? XP1 + XP2 : (lane == 1 ? XP2 : (lane == 2 ? 0u : 0u - XP1));
+    const uint4* g = reinterpret_cast<const uint4*>(p);
+    // Four rows (2 KiB) in flight per warp — a single warp has to cover the memory latency by itself — held in four
+    // registers that are never copied into each other (a rotation would wait for the newest load every row).
+    uint4 nq[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) nq[j] = (uint64_t)lane + 32 * j < stripes ? __ldcg(g + lane + 32 * j) : make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    auto one_row = [&](uint64_t r, uint4& q) {
+        uint32_t* row = rows + (r & 1) * 128;
+        // every lane pre-multiplies its four words by P2 (off the hashing lanes' critical path)
+        row[lane] = q.x * XP2; row[32 + lane] = q.y * XP2; row[64 + lane] = q.z * XP2; row[96 + lane] = q.w * XP2;
+        const uint64_t s1 = (r + 4) * 32 + lane;
+        if (s1 < stripes) q = __ldcg(g + s1);
+        __syncwarp();
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, stripes - r * 32);
+        if (lane < 4) {
+            uint32_t w[32];
+            const uint4* mine = reinterpret_cast<const uint4*>(row + lane * 32);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint4 t = mine[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
+            if (cnt == 32) {
+                uint32_t sv = acc + w[0];
+#pragma unroll
+                for (int k = 1; k < 32; k++) sv = (sv >> 19) * XP1 + (sv * K13 + w[k]);
+                acc = rotl32(sv, 13) * XP1;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; k++)
+                    if ((uint32_t)k < cnt) acc = rotl32(acc + w[k], 13) * XP1;
+            }
+        }
+        // rows alternate between two buffers; a buffer is rewritten only after the __syncwarp of the row in between
+    };
+    uint64_t r = 0;
+    for (; r + 4 <= nrows; r += 4) {
+        one_row(r, nq[0]); one_row(r + 1, nq[1]); one_row(r + 2, nq[2]); one_row(r + 3, nq[3]);
+    }
+    if (r < nrows) one_row(r, nq[0]);
+    if (r + 1 < nrows) one_row(r + 1, nq[1]);
+    if (r + 2 < nrows) one_row(r + 2, nq[2]);
+    const uint32_t v1 = __shfl_sync(FULL, acc, 0), v2 = __shfl_sync(FULL, acc, 1), v3 = __shfl_sync(FULL, acc, 2), v4 = __shfl_sync(FULL, acc, 3);
+    uint32_t h = L >= 16 ? rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18) : XP5;
+    h += (uint32_t)L;
+    if (lane == 0) {
+        uint64_t b = stripes * 16;
+        while (b + 4 <= L) { h = rotl32(h + __ldcg(reinterpret_cast<const uint32_t*>(p + b)) * XP3, 17) * XP4; b += 4; }
+        while (b < L) { h = rotl32(h + (uint32_t)__ldcg(p + b) * XP5, 11) * XP1; b++; }
+        h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+    }
+    __syncwarp();
+    return __shfl_sync(FULL, h, 0);
+}
+
+constexpr int XXH_WARPS = 4;
+__global__ void __launch_bounds__(XXH_WARPS * 32) xxh32_units_kernel(uint32_t n, const uint8_t* __restrict__ base, const uint64_t* __restrict__ off,
+                                                                      const uint64_t* __restrict__ len, uint32_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t rows[XXH_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t u = blockIdx.x * XXH_WARPS + warp;
     if (u >= n) return;
     const uint8_t* p = base + off[u];
-    if (((uintptr_t)p & 15) == 0) out[u] = xxh32_global(p, len[u]);
-    else out[u] = xxh32_generic([&](uint64_t q) { return __ldcg(p + q); }, len[u], 0);
+    const uint64_t L = len[u];
+    uint32_t h;
+    if (((uintptr_t)p & 15) != 0) {  // unaligned unit: byte-wise, one lane (engine-made arenas are aligned)
+        h = lane == 0 ? xxh32_generic([&](uint64_t q) { return __ldcg(p + q); }, L, 0) : 0u;
+    } else {
+        h = xxh32_warp(p, L, rows[warp], lane);
+    }
+    if (lane == 0) out[u] = h;
 }
 
 // CRC-32C (Castagnoli), slicing-by-8 tables built in shared memory by each CTA; one thread per unit.
@@ -201,8 +281,14 @@ __device__ int32_t lz4f_decode_stream(const uint8_t* __restrict__ src, uint32_t 
             if (n - ip < 4) { st = CJ_ST_TRUNCATED; break; }
             out.flush_to(out.op, true);
             uint32_t h = 0;
-            if (lane == 0) h = xxh32_global(dst + frame_start, out.op - frame_start);
-            h = __shfl_sync(FULL, h, 0);
+            const uint8_t* fp = dst + frame_start;
+            if (((uintptr_t)fp & 15) == 0) {   // the ring is idle between frames: its first KiB parks the rows being hashed
+                __threadfence_block();
+                h = xxh32_warp(fp, out.op - frame_start, reinterpret_cast<uint32_t*>(smem_warp), lane);
+            } else {
+                if (lane == 0) h = xxh32_global(fp, out.op - frame_start);
+                h = __shfl_sync(FULL, h, 0);
+            }
             if (h != rd32g(src + ip)) { st = CJ_ST_CHECKSUM; break; }
             ip += 4;
         }
@@ -257,6 +343,23 @@ cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, 
 // Host plumbing
 // ================================================================================================
 namespace {
+
+// CJ_TRACE=1: wall-clock checkpoints of the frame paths on stderr (each one drains the stream first).
+struct PhaseTrace {
+    cj_ctx* c;
+    const char* what;
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    PhaseTrace(cj_ctx* c_, const char* w) : c(c_), what(w), on(getenv("CJ_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char* label) {
+        if (!on) return;
+        cudaStreamSynchronize(c->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cj] %s: %-28s +%8.2f ms (total %8.2f)\n", what, label, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
 
 inline uint32_t h_rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline void h_wr32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
@@ -360,7 +463,7 @@ int launch_crc(cj_ctx* c, uint32_t n, const uint8_t* base, const uint64_t* off, 
 
 int launch_xxh32(cj_ctx* c, uint32_t n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t* out) {
     if (!n) return CJ_OK;
-    xxh32_units_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(n, base, off, len, out);
+    xxh32_units_kernel<<<(n + XXH_WARPS - 1) / XXH_WARPS, XXH_WARPS * 32, 0, c->stream>>>(n, base, off, len, out);
     c->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return CJ_OK;
@@ -430,6 +533,7 @@ int32_t snappy_frame_walk(const uint8_t* s, size_t n, std::vector<SnChunk>* chun
 }
 
 int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
+    PhaseTrace tr(c, "snappy_framed_decompress");
     const size_t n = bt->n;
     const uint8_t* hs = (const uint8_t*)bt->src_base;
     std::vector<uint64_t> sbase, dbase(n);
@@ -519,6 +623,7 @@ int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
 }
 
 int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
+    PhaseTrace tr(c, "snappy_framed_compress");
     const size_t n = bt->n;
     static const uint8_t STREAM_ID[10] = {0xff, 0x06, 0x00, 0x00, 's', 'N', 'a', 'P', 'p', 'Y'};
     std::vector<uint64_t> sbase;
@@ -605,11 +710,15 @@ int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // descriptor scratch is reused by the next splice
         return CJ_OK;
     };
+    tr.mark("host layout");
     if ((rc = splice(hdr, (const uint8_t*)c->f_ddst.p, blob_off))) return rc;
     if ((rc = splice(body_comp, (const uint8_t*)c->f_dtmp.p, 0))) return rc;
     if ((rc = splice(body_raw, (const uint8_t*)c->f_dsrc.p, 0))) return rc;
+    tr.mark("splice");
     for (size_t i = 0; i < n; i++) bt->dst_len[i] = bt->status[i] == CJ_OK ? total[i] : 0;
-    return download_units(c, bt, where, dbase, dacc);
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
 }
 
 // ---- LZ4 frame compress: independent 64 KiB blocks + content checksum --------------------------------
@@ -619,7 +728,9 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
     const size_t n = bt->n;
     std::vector<uint64_t> sbase;
     int rc;
+    PhaseTrace tr(c, "lz4f_compress");
     if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    tr.mark("upload");
     const size_t slot = cj_align16(65536 + 65536 / 255 + 16);
     Items ch, whole;
     for (size_t i = 0; i < n; i++) {
@@ -655,7 +766,9 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = dch.dof; b.dst_cap = dch.dc; b.dst_len = dch.dl; b.status = dch.st;
         if ((rc = cj_run_device_batch(c, CJ_LZ4_BLOCK, true, b, &blk))) return rc;
     }
+    tr.mark("items + block encode");
     if ((rc = launch_xxh32(c, (uint32_t)n, (const uint8_t*)c->f_dsrc.p, dwhole.so, dwhole.sl, dwhole.aux))) return rc;
+    tr.mark("content xxh32");
     if ((rc = fetch_results(c, dch))) return rc;
     if ((rc = fetch_results(c, dwhole))) return rc;
     const uint64_t* clen = dch.h + 4 * nc;
@@ -717,11 +830,244 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         return CJ_OK;
     };
+    tr.mark("host layout");
     if ((rc = splice(hdr, (const uint8_t*)c->f_ddst.p, blob_off))) return rc;
     if ((rc = splice(body_comp, (const uint8_t*)c->f_dtmp.p, 0))) return rc;
     if ((rc = splice(body_raw, (const uint8_t*)c->f_dsrc.p, 0))) return rc;
+    tr.mark("splice");
     for (size_t i = 0; i < n; i++) bt->dst_len[i] = bt->status[i] == CJ_OK ? total[i] : 0;
-    return download_units(c, bt, where, dbase, dacc);
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
+}
+
+// ---- LZ4 frame decompress: block-parallel for independent-block frames --------------------------
+// The warp-per-frame kernel (lz4f_decode_kernel) decodes one frame's blocks one after the other — right for batches
+// of many frames and the only option for linked blocks, but a single large frame would run on one warp (62 MB/s).
+// Frames whose descriptor says "independent blocks" (what this engine's own encoder and the lz4 CLI write) are cut
+// into block units on the host (headers only), decoded by the batched block kernels into fixed slots, spliced into
+// place with a device copy, and their block / content checksums computed by xxh32_units_kernel.  A unit with anything
+// unusual in it (a failed block, a checksum or size mismatch, a malformed or linked frame) is handed to the
+// warp-per-frame kernel, which owns the exact status codes.
+struct Lz4fBlock { uint64_t payload_off; uint32_t len; bool stored; bool has_sum; uint32_t want_sum; };
+struct Lz4fFrame { uint32_t bmax; bool has_csum, has_csize; uint32_t want_csum; uint64_t csize; size_t first_block, n_blocks; };
+
+// Returns true if every frame of the stream is a well-formed independent-block frame (skippable frames are stepped over).
+bool lz4f_plan_host(const uint8_t* s, size_t n, std::vector<Lz4fFrame>& frames, std::vector<Lz4fBlock>& blocks) {
+    size_t ip = 0;
+    while (ip < n) {
+        if (n - ip < 4) return false;
+        const uint32_t magic = h_rd32(s + ip);
+        if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {
+            if (n - ip < 8) return false;
+            const uint32_t sz = h_rd32(s + ip + 4);
+            if (sz > n - ip - 8) return false;
+            ip += 8 + (size_t)sz;
+            continue;
+        }
+        if (magic != 0x184D2204u || n - ip < 7) return false;
+        const uint32_t flg = s[ip + 4], bd = s[ip + 5];
+        if ((flg >> 6) != 1 || (flg & 0x02) || (bd & 0x8F)) return false;
+        const bool indep = (flg >> 5) & 1, bsum = (flg >> 4) & 1, csize = (flg >> 3) & 1, csum = (flg >> 2) & 1, dict = flg & 1;
+        const uint32_t bid = (bd >> 4) & 7;
+        if (!indep || dict || bid < 4) return false;
+        const uint32_t dlen = 2 + (csize ? 8 : 0);
+        if (n - ip < 4 + dlen + 1) return false;
+        if (((h_xxh32(s + ip + 4, dlen) >> 8) & 0xff) != s[ip + 4 + dlen]) return false;
+        Lz4fFrame f{};
+        f.bmax = 1u << (8 + 2 * bid);
+        f.has_csum = csum; f.has_csize = csize;
+        if (csize) memcpy(&f.csize, s + ip + 6, 8);
+        f.first_block = blocks.size();
+        ip += 4 + dlen + 1;
+        for (;;) {
+            if (n - ip < 4) return false;
+            const uint32_t bs = h_rd32(s + ip);
+            ip += 4;
+            if (bs == 0) break;
+            const uint32_t blen = bs & 0x7FFFFFFFu;
+            if (blen > f.bmax || blen > n - ip || blen == 0) return false;
+            Lz4fBlock b{ip, blen, (bs >> 31) != 0, bsum, 0};
+            if (bsum) {
+                if (n - ip - blen < 4) return false;
+                b.want_sum = h_rd32(s + ip + blen);
+            }
+            blocks.push_back(b);
+            ip += (size_t)blen + (bsum ? 4 : 0);
+        }
+        f.n_blocks = blocks.size() - f.first_block;
+        if (csum) {
+            if (n - ip < 4) return false;
+            f.want_csum = h_rd32(s + ip);
+            ip += 4;
+        }
+        frames.push_back(f);
+    }
+    return true;
+}
+
+// Sequentially carves descriptor groups out of ctx->f_ddesc / f_hdesc (sized up front).
+struct DescCarver {
+    cj_ctx* c;
+    size_t off = 0;
+    static size_t bytes_for(size_t n) { return cj_align16(n * (48 + 8) + 64); }
+    int put(const Items& it, DevItems* out) {
+        Scratch ds, hs2;
+        ds.p = (uint8_t*)c->f_ddesc.p + off; ds.cap = c->f_ddesc.cap - off;
+        hs2.p = (uint8_t*)c->f_hdesc.p + off; hs2.cap = c->f_hdesc.cap - off; hs2.pinned = true;
+        const int r = upload_items(c, it, ds, hs2, out);
+        ds.p = nullptr; hs2.p = nullptr;  // not owned
+        off += bytes_for(it.size());
+        return r;
+    }
+};
+
+int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
+    const size_t n = bt->n;
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    std::vector<uint64_t> sbase, dbase(n);
+    int rc;
+    PhaseTrace tr(c, "lz4f_decompress");
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    tr.mark("upload");
+    size_t dacc = 0;
+    for (size_t i = 0; i < n; i++) { dbase[i] = dacc; dacc += cj_align16((size_t)bt->dst_cap[i]); bt->dst_len[i] = 0; bt->status[i] = CJ_OK; }
+    if ((rc = c->f_ddst.ensure(dacc + 64))) return rc;
+
+    // plan: which units go block-parallel
+    std::vector<std::vector<Lz4fFrame>> frames(n);
+    std::vector<std::vector<Lz4fBlock>> blocks(n);
+    std::vector<char> par(n, 0);
+    size_t nblk = 0, nfr = 0, slot_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (bt->src_len[i] > MAX_UNIT || bt->dst_cap[i] > MAX_UNIT) continue;
+        if (bt->src_len[i] < (1u << 17)) continue;   // small streams: one warp is as good
+        if (!lz4f_plan_host(hs + bt->src_off[i], (size_t)bt->src_len[i], frames[i], blocks[i]) || blocks[i].size() < 2) continue;
+        par[i] = 1;
+        nblk += blocks[i].size();
+        nfr += frames[i].size();
+    }
+    Items dec, sums;          // compressed blocks -> temp slots; block checksums over compressed payloads
+    std::vector<size_t> dec_of(0), sum_of(0);   // per block (flattened over parallel units): index into dec / sums or ~0
+    for (size_t i = 0; i < n; i++) {
+        if (!par[i]) continue;
+        for (const Lz4fFrame& f : frames[i])
+            for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++) {
+                const Lz4fBlock& b = blocks[i][k];
+                if (!b.stored) { dec_of.push_back(dec.size()); dec.add(sbase[i] + b.payload_off, b.len, slot_bytes, f.bmax); slot_bytes += cj_align16(f.bmax); }
+                else dec_of.push_back(~(size_t)0);
+                if (b.has_sum) { sum_of.push_back(sums.size()); sums.add(sbase[i] + b.payload_off, b.len, 0, 0); }
+                else sum_of.push_back(~(size_t)0);
+            }
+    }
+    std::vector<char> serial(n, 0);
+    for (size_t i = 0; i < n; i++) serial[i] = !par[i];
+    if (nblk) {
+        if ((rc = c->f_dtmp.ensure(slot_bytes + 64))) return rc;
+        const size_t need = DescCarver::bytes_for(dec.size()) + DescCarver::bytes_for(sums.size()) + 2 * DescCarver::bytes_for(nblk) + DescCarver::bytes_for(nfr) + 256;
+        if ((rc = c->f_ddesc.ensure(need))) return rc;
+        if ((rc = c->f_hdesc.ensure(need))) return rc;
+        DescCarver carve{c};
+        DevItems ddec, dsums;
+        if ((rc = carve.put(dec, &ddec))) return rc;
+        if ((rc = carve.put(sums, &dsums))) return rc;
+        if (dec.size()) {
+            Batch b;
+            b.n = (uint32_t)dec.size();
+            b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = ddec.so; b.src_len = ddec.sl;
+            b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = ddec.dof; b.dst_cap = ddec.dc; b.dst_len = ddec.dl; b.status = ddec.st;
+            if ((rc = cj_run_device_batch(c, CJ_LZ4_BLOCK, false, b, nullptr))) return rc;
+        }
+        if ((rc = launch_xxh32(c, (uint32_t)sums.size(), (const uint8_t*)c->f_dsrc.p, dsums.so, dsums.sl, dsums.aux))) return rc;
+        if ((rc = fetch_results(c, ddec))) return rc;
+        if ((rc = fetch_results(c, dsums))) return rc;
+        tr.mark("plan + block decode");
+        const uint64_t* bdl = ddec.h + 4 * ddec.n;
+        const int32_t* bst = (const int32_t*)(ddec.h + 5 * ddec.n);
+        const uint32_t* bsum = (const uint32_t*)((const int32_t*)(dsums.h + 5 * dsums.n) + dsums.n);
+        // place every block; anything unusual sends the whole unit to the warp-per-frame kernel
+        Items mv_dec, mv_raw, whole;      // temp slot -> final, stored payload -> final, frames to checksum
+        std::vector<uint32_t> whole_want, whole_owner;
+        size_t flat = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (!par[i]) continue;
+            uint64_t pos = 0;
+            bool ok = true;
+            const size_t m0 = mv_dec.size(), r0 = mv_raw.size(), w0 = whole.size();
+            for (const Lz4fFrame& f : frames[i]) {
+                const uint64_t fstart = pos;
+                for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++, flat++) {
+                    const Lz4fBlock& b = blocks[i][k];
+                    if (!ok) continue;
+                    if (b.has_sum && bsum[sum_of[flat]] != b.want_sum) { ok = false; continue; }
+                    uint64_t produced;
+                    if (b.stored) {
+                        produced = b.len;
+                        if (pos + produced > bt->dst_cap[i]) { ok = false; continue; }
+                        mv_raw.add(sbase[i] + b.payload_off, produced, dbase[i] + pos, 0);
+                    } else {
+                        const size_t d = dec_of[flat];
+                        if (bst[d] != CJ_OK) { ok = false; continue; }
+                        produced = bdl[d];
+                        if (pos + produced > bt->dst_cap[i]) { ok = false; continue; }
+                        mv_dec.add(dec.dof[d], produced, dbase[i] + pos, 0);
+                    }
+                    pos += produced;
+                }
+                if (ok && f.has_csize && f.csize != pos - fstart) ok = false;
+                if (ok && f.has_csum) { whole.add(dbase[i] + fstart, pos - fstart, 0, 0); whole_want.push_back(f.want_csum); whole_owner.push_back((uint32_t)i); }
+            }
+            if (!ok) {
+                serial[i] = 1;
+                mv_dec.so.resize(m0); mv_dec.sl.resize(m0); mv_dec.dof.resize(m0); mv_dec.dc.resize(m0);
+                mv_raw.so.resize(r0); mv_raw.sl.resize(r0); mv_raw.dof.resize(r0); mv_raw.dc.resize(r0);
+                whole.so.resize(w0); whole.sl.resize(w0); whole.dof.resize(w0); whole.dc.resize(w0);
+                whole_want.resize(w0); whole_owner.resize(w0);
+            } else {
+                bt->dst_len[i] = pos;
+            }
+        }
+        DevItems dmv, draw, dwhole;
+        if ((rc = carve.put(mv_dec, &dmv))) return rc;
+        if ((rc = carve.put(mv_raw, &draw))) return rc;
+        if ((rc = carve.put(whole, &dwhole))) return rc;
+        if ((rc = copy_units(c, (uint32_t)mv_dec.size(), (const uint8_t*)c->f_dtmp.p, dmv.so, dmv.sl, (uint8_t*)c->f_ddst.p, dmv.dof))) return rc;
+        if ((rc = copy_units(c, (uint32_t)mv_raw.size(), (const uint8_t*)c->f_dsrc.p, draw.so, draw.sl, (uint8_t*)c->f_ddst.p, draw.dof))) return rc;
+        tr.mark("place blocks");
+        if ((rc = launch_xxh32(c, (uint32_t)whole.size(), (const uint8_t*)c->f_ddst.p, dwhole.so, dwhole.sl, dwhole.aux))) return rc;
+        if ((rc = fetch_results(c, dwhole))) return rc;
+        tr.mark("content xxh32");
+        const uint32_t* got = (const uint32_t*)((const int32_t*)(dwhole.h + 5 * dwhole.n) + dwhole.n);
+        for (size_t k = 0; k < whole.size(); k++)
+            if (got[k] != whole_want[k]) { serial[whole_owner[k]] = 1; bt->dst_len[whole_owner[k]] = 0; }
+    }
+    // everything else (and every unit that tripped a check above): one warp per frame stream, exact status codes
+    Items ser;
+    std::vector<size_t> ser_unit;
+    for (size_t i = 0; i < n; i++)
+        if (serial[i]) { ser.add(sbase[i], bt->src_len[i], dbase[i], bt->dst_cap[i]); ser_unit.push_back(i); }
+    if (ser.size()) {
+        const size_t need = DescCarver::bytes_for(ser.size()) + 64;
+        // results of the parallel part are already on the host: the descriptor scratch can be reused
+        if ((rc = c->f_ddesc.ensure(need))) return rc;
+        if ((rc = c->f_hdesc.ensure(need))) return rc;
+        DescCarver carve{c};
+        DevItems dser;
+        if ((rc = carve.put(ser, &dser))) return rc;
+        Batch b;
+        b.n = (uint32_t)ser.size();
+        b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = dser.so; b.src_len = dser.sl;
+        b.dst_base = (uint8_t*)c->f_ddst.p; b.dst_off = dser.dof; b.dst_cap = dser.dc; b.dst_len = dser.dl; b.status = dser.st;
+        if ((rc = cj_run_device_batch(c, CJ_LZ4_FRAME, false, b, nullptr))) return rc;
+        if ((rc = fetch_results(c, dser))) return rc;
+        const uint64_t* dl = dser.h + 4 * dser.n;
+        const int32_t* st = (const int32_t*)(dser.h + 5 * dser.n);
+        for (size_t k = 0; k < ser.size(); k++) { bt->dst_len[ser_unit[k]] = st[k] == CJ_OK ? dl[k] : 0; bt->status[ser_unit[k]] = st[k]; }
+    }
+    tr.mark("serial units");
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
 }
 
 }  // namespace
@@ -733,6 +1079,7 @@ int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
     }
     if (bt->n == 0) return CJ_OK;
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_decompress(c, where, bt);
+    if (codec == CJ_LZ4_FRAME) return lz4f_decompress(c, where, bt);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }
