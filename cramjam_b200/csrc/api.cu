@@ -428,6 +428,13 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     CUDA_TRY(cudaSetDevice(c->device));
     if (codec == CJ_SNAPPY_FRAMED || (codec == CJ_LZ4_FRAME && (compress || where != CJ_DEVICE)))
         return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
+    // Zstandard with host-visible buffers: large inputs are compressed as several frames, multi-frame streams are decoded one
+    // frame per warp (frames.cu); batches of small single-frame units keep the plain one-warp-per-unit plumbing below
+    if (codec == CJ_ZSTD && where != CJ_DEVICE && bt->n) {
+        bool big = false;
+        for (size_t i = 0; i < bt->n && !big; i++) big = bt->src_len[i] > (compress ? (512u << 10) : (128u << 10));
+        if (big) return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
+    }
     // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
     if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME && codec != CJ_ZSTD) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }
     if (where == CJ_DEVICE) {

@@ -1070,6 +1070,159 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
     return rc;
 }
 
+// ---- Zstandard through the single-buffer API ---------------------------------------------------
+// The zstd kernels run one warp per frame, which is the right unit for batches of frames but leaves a single large
+// buffer on one warp.  Compress: inputs larger than ZS_PIECE are written as a sequence of independent frames of
+// ZS_PIECE bytes each (concatenated frames are one valid Zstandard stream — zstd::stream::read::Decoder, which the
+// reference's decompress uses (src/zstd.rs:23-28), and ZSTD_decompress read them back to back; the encoder's
+// match window is 64 KiB, so the split costs almost no ratio), compressed by as many warps.  Decompress: the host
+// walks the frame headers; a stream of two or more frames that all declare their content size is decoded one frame
+// per warp straight into its final position.  Anything else, and any stream whose frames do not all come back
+// clean and exactly sized, goes through the whole-stream path, which owns the exact status codes.
+constexpr size_t ZS_PIECE = 512 * 1024;
+
+int zstd_compress_split(cj_ctx* c, int where, const cj_batch* bt, const cj_params* params) {
+    const size_t n = bt->n;
+    PhaseTrace tr(c, "zstd_compress");
+    std::vector<uint64_t> sbase, dbase(n);
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    tr.mark("upload");
+    Items enc;
+    std::vector<size_t> first(n + 1, 0);
+    size_t slot_acc = 0;
+    for (size_t i = 0; i < n; i++) {
+        first[i] = enc.size();
+        const uint64_t L = bt->src_len[i];
+        uint64_t p = 0;
+        do {
+            const uint64_t len = std::min<uint64_t>(ZS_PIECE, L - p);
+            const size_t cap = cj_align16(cj_compress_bound(CJ_ZSTD, (size_t)len));
+            enc.add(sbase[i] + p, len, slot_acc, cap);
+            slot_acc += cap;
+            p += len;
+        } while (p < L);
+    }
+    first[n] = enc.size();
+    if ((rc = c->f_dtmp.ensure(slot_acc + 64))) return rc;
+    const size_t need = 2 * DescCarver::bytes_for(enc.size()) + 128;
+    if ((rc = c->f_ddesc.ensure(need))) return rc;
+    if ((rc = c->f_hdesc.ensure(need))) return rc;
+    DescCarver carve{c};
+    DevItems denc;
+    if ((rc = carve.put(enc, &denc))) return rc;
+    Batch b;
+    b.n = (uint32_t)enc.size();
+    b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = denc.so; b.src_len = denc.sl;
+    b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = denc.dof; b.dst_cap = denc.dc; b.dst_len = denc.dl; b.status = denc.st;
+    if ((rc = cj_run_device_batch(c, CJ_ZSTD, true, b, params))) return rc;
+    if ((rc = fetch_results(c, denc))) return rc;
+    tr.mark("frames encoded");
+    const uint64_t* dl = denc.h + 4 * denc.n;
+    const int32_t* st = (const int32_t*)(denc.h + 5 * denc.n);
+    Items mv;
+    size_t dacc = 0;
+    for (size_t i = 0; i < n; i++) {
+        dbase[i] = dacc;
+        bt->status[i] = CJ_OK;
+        uint64_t pos = 0;
+        for (size_t k = first[i]; k < first[i + 1]; k++) {
+            if (st[k] != CJ_OK && bt->status[i] == CJ_OK) bt->status[i] = st[k];
+            pos += dl[k];
+        }
+        if (bt->status[i] == CJ_OK && pos > bt->dst_cap[i]) bt->status[i] = CJ_ST_DST_SMALL;
+        bt->dst_len[i] = bt->status[i] == CJ_OK ? pos : 0;
+        if (bt->status[i] != CJ_OK) continue;
+        pos = 0;
+        for (size_t k = first[i]; k < first[i + 1]; k++) { mv.add(enc.dof[k], dl[k], dacc + pos, 0); pos += dl[k]; }
+        dacc += cj_align16((size_t)pos);
+    }
+    if ((rc = c->f_ddst.ensure(dacc + 64))) return rc;
+    DevItems dmv;
+    if ((rc = carve.put(mv, &dmv))) return rc;
+    if ((rc = copy_units(c, (uint32_t)mv.size(), (const uint8_t*)c->f_dtmp.p, dmv.so, dmv.sl, (uint8_t*)c->f_ddst.p, dmv.dof))) return rc;
+    tr.mark("splice");
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
+}
+
+int zstd_decompress_frames(cj_ctx* c, int where, const cj_batch* bt) {
+    const size_t n = bt->n;
+    const uint8_t* hs = (const uint8_t*)bt->src_base;
+    PhaseTrace tr(c, "zstd_decompress");
+    std::vector<uint64_t> sbase, dbase(n);
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    tr.mark("upload");
+    size_t dacc = 0;
+    for (size_t i = 0; i < n; i++) { dbase[i] = dacc; dacc += cj_align16((size_t)bt->dst_cap[i]); bt->dst_len[i] = 0; bt->status[i] = CJ_OK; }
+    if ((rc = c->f_ddst.ensure(dacc + 64))) return rc;
+    // pass 0: frame-parallel where the headers allow it, whole stream otherwise; pass 1: whole stream for every unit that tripped
+    std::vector<char> par(n, 0), redo(n, 0);
+    std::vector<std::vector<cj_frame_info>> frames(n);
+    for (size_t i = 0; i < n; i++) {
+        if (bt->src_len[i] > MAX_UNIT || bt->dst_cap[i] > MAX_UNIT) continue;
+        size_t tot = 0;
+        bool exact = false;
+        if (cj_zstd_walk_host(hs + bt->src_off[i], (size_t)bt->src_len[i], &tot, &exact, &frames[i]) != CJ_OK || !exact || tot > bt->dst_cap[i]) continue;
+        size_t real = 0;   // frames that are not skippable (exact == true: every one of them declares its content size)
+        for (const cj_frame_info& f : frames[i]) {
+            uint32_t magic; memcpy(&magic, hs + bt->src_off[i] + f.offset, 4);
+            if ((magic & 0xFFFFFFF0u) != 0x184D2A50u) real++;
+        }
+        if (real >= 2) par[i] = 1;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        Items it;
+        std::vector<uint32_t> owner;
+        for (size_t i = 0; i < n; i++) {
+            if (pass == 0 && par[i]) {
+                uint64_t pos = 0;
+                for (const cj_frame_info& f : frames[i]) {
+                    uint32_t magic; memcpy(&magic, hs + bt->src_off[i] + f.offset, 4);
+                    if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) continue;   // skippable frame: nothing to decode
+                    it.add(sbase[i] + f.offset, f.size, dbase[i] + pos, f.content);
+                    owner.push_back((uint32_t)i);
+                    pos += f.content;
+                }
+                bt->dst_len[i] = pos;
+            } else if ((pass == 0 && !par[i]) || (pass == 1 && redo[i])) {
+                it.add(sbase[i], bt->src_len[i], dbase[i], bt->dst_cap[i]);
+                owner.push_back((uint32_t)i);
+            }
+        }
+        if (!it.size()) continue;
+        const size_t need = DescCarver::bytes_for(it.size()) + 64;
+        if ((rc = c->f_ddesc.ensure(need))) return rc;
+        if ((rc = c->f_hdesc.ensure(need))) return rc;
+        DescCarver carve{c};
+        DevItems d;
+        if ((rc = carve.put(it, &d))) return rc;
+        Batch b;
+        b.n = (uint32_t)it.size();
+        b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = d.so; b.src_len = d.sl;
+        b.dst_base = (uint8_t*)c->f_ddst.p; b.dst_off = d.dof; b.dst_cap = d.dc; b.dst_len = d.dl; b.status = d.st;
+        if ((rc = cj_run_device_batch(c, CJ_ZSTD, false, b, nullptr))) return rc;
+        if ((rc = fetch_results(c, d))) return rc;
+        tr.mark(pass == 0 ? "frames decoded" : "whole-stream redo");
+        const uint64_t* dl = d.h + 4 * d.n;
+        const int32_t* st = (const int32_t*)(d.h + 5 * d.n);
+        for (size_t k = 0; k < it.size(); k++) {
+            const uint32_t u = owner[k];
+            if (pass == 0 && par[u]) {
+                if (st[k] != CJ_OK || dl[k] != it.dc[k]) redo[u] = 1;
+            } else {
+                bt->status[u] = st[k];
+                bt->dst_len[u] = st[k] == CJ_OK ? dl[k] : 0;
+            }
+        }
+    }
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
+}
+
 }  // namespace
 
 int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
@@ -1080,6 +1233,7 @@ int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
     if (bt->n == 0) return CJ_OK;
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_decompress(c, where, bt);
     if (codec == CJ_LZ4_FRAME) return lz4f_decompress(c, where, bt);
+    if (codec == CJ_ZSTD) return zstd_decompress_frames(c, where, bt);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }
@@ -1092,6 +1246,7 @@ int frames_compress(cj_ctx* c, int codec, int where, const cj_batch* bt, const c
     if (bt->n == 0) return CJ_OK;
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_compress(c, where, bt);
     if (codec == CJ_LZ4_FRAME) return lz4f_compress(c, where, bt, params);
+    if (codec == CJ_ZSTD) return zstd_compress_split(c, where, bt, params);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }

@@ -365,6 +365,8 @@ static int64_t lz4f_walk(const uint8_t* src, size_t n, uint8_t* dst, size_t cap,
                 uint8_t* win = indep ? dst + d : dst + frame_start;
                 size_t room = cap - d < bmax ? cap - d : bmax;
                 int64_t r = lz4_block_decode_linked(src + s, blen, win, dst + d, room);
+                /* a block that outgrows the frame's own block size is a format violation, not a capacity problem of the caller */
+                if (r == ERR(CJO_E_DST_SMALL) && room == bmax) return ERR(CJO_E_CORRUPT);
                 if (r < 0) return r;
                 d += (size_t)r;
             }

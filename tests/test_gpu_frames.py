@@ -11,7 +11,7 @@ import corpus
 import oracle as O
 import syslibs as S
 from cramjam_b200 import _capi as capi
-from gpu_util import ctx
+from gpu_util import assert_same_as_oracle, ctx
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -134,3 +134,29 @@ def test_decompress_bound_values():
     rc, v = bound(capi.LZ4_FRAME, O.lz4f_compress(d, 1 | 2))       # no content size: an upper bound
     assert rc == 0 and v >= len(d)
     assert bound(capi.SNAPPY_FRAMED, b"sknow")[0] != 0
+
+
+def test_lz4f_large_frames_block_parallel_path_matches_oracle():
+    """Frames of >= 128 KiB with independent blocks take the block-parallel decode (frames.cu lz4f_decompress); linked
+    frames, corrupted frames and short capacities must still give the oracle's bytes and status codes."""
+    if not S.have_lz4:
+        pytest.skip("no liblz4")
+    data = capi.synth_host(20, 65536, seed=11, first_index=9).tobytes() + b"xyz" * 777
+    rng = np.random.default_rng(17)
+    units, caps = [], []
+    for kw in (dict(independent=True), dict(independent=True, block_checksum=True), dict(independent=True, content_checksum=False),
+               dict(independent=False), dict(independent=True, block_size_id=5), dict(independent=True, level=9)):
+        f = S.lz4f_compress(data, **kw)
+        units += [f, f, f + f, f[:-2]]
+        caps += [len(data), len(data) - 1, 2 * len(data), len(data)]
+        for _ in range(10):
+            m = bytearray(f)
+            m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            units.append(bytes(m)); caps.append(len(data))
+    assert_same_as_oracle(capi.LZ4_FRAME, units, caps, "host")
+    # and the engine's own frames (independent blocks, content size + checksum)
+    bound = capi.lib().cj_compress_bound(capi.LZ4_FRAME, len(data))
+    enc, st = ctx().run_host_units(capi.LZ4_FRAME, True, [data], [bound])
+    assert st[0] == 0
+    outs, st = ctx().run_host_units(capi.LZ4_FRAME, False, enc, [len(data)])
+    assert st[0] == 0 and outs[0] == data

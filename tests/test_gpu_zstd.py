@@ -116,3 +116,30 @@ def test_zstd_encode_compresses_and_is_deterministic():
     d = corpus.text(5000, 1)
     small, st = ctx().run_host_units(capi.ZSTD, True, [d], [10])
     assert st[0] == 5                                           # DST_SMALL
+
+
+def test_large_single_buffer_round_trip_is_multi_frame_and_libzstd_readable():
+    """Inputs above 512 KiB are written as concatenated independent frames (one warp each) and read back
+    frame-parallel; libzstd and the oracle must read the stream, and a libzstd-made multi-frame stream must decode."""
+    data = capi.synth_host(48, 65536, seed=7, first_index=3).tobytes() + b"tail" * 1000   # 3 MiB + 4000 B
+    bound = capi.lib().cj_compress_bound(capi.ZSTD, len(data))
+    enc, st = ctx().run_host_units(capi.ZSTD, True, [data, data[:700000], b""], [bound, bound, 64])
+    assert (st == 0).all()
+    assert enc[0].count(b"\x28\xb5\x2f\xfd") >= 7          # 3 MiB + tail -> 7 frames
+    for c, d in zip(enc, (data, data[:700000], b"")):
+        assert O.zstd_decompress(c) == d
+        if S.have_zstd:
+            assert S.zstd_decompress(c, len(d)) == d
+    outs, st = ctx().run_host_units(capi.ZSTD, False, enc, [len(data), 700000, 0])
+    assert (st == 0).all() and outs[0] == data and outs[1] == data[:700000] and outs[2] == b""
+    if S.have_zstd:
+        multi = b"".join(S.zstd_compress(data[i:i + 300000], 3) for i in range(0, len(data), 300000))
+        skippable = b"\x50\x2a\x4d\x18" + (5).to_bytes(4, "little") + b"hello"
+        stream = skippable + multi
+        rng = np.random.default_rng(5)
+        units, caps = [stream, stream, stream[:-3], multi + b"\x00"], [len(data), len(data) - 1, len(data), len(data)]
+        for _ in range(24):   # corrupt one byte somewhere: the frame-parallel path must hand over to the whole-stream path
+            m = bytearray(stream)
+            m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            units.append(bytes(m)); caps.append(len(data))
+        assert_same_as_oracle(capi.ZSTD, units, caps, "host")
