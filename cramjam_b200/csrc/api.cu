@@ -141,7 +141,9 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
         return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16;
     }
     case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8;
-    case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18;  // a block that does not shrink is stored raw: header + 3 bytes per block
+    // a block that does not shrink is stored raw: header + 3 bytes per block; inputs above 64 KiB are written as several
+    // frames of >= 64 KiB each (frames.cu zstd_compress_split): one more frame header + block header per piece
+    case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18 + (n / 65536) * 24;
     default: return 0;
     }
 }
@@ -432,8 +434,14 @@ static int run_batch(cj_ctx* c, int codec, bool compress, int where, const cj_ba
     // frame per warp (frames.cu); batches of small single-frame units keep the plain one-warp-per-unit plumbing below
     if (codec == CJ_ZSTD && where != CJ_DEVICE && bt->n) {
         bool big = false;
-        for (size_t i = 0; i < bt->n && !big; i++) big = bt->src_len[i] > (compress ? (512u << 10) : (128u << 10));
+        for (size_t i = 0; i < bt->n && !big; i++) big = bt->src_len[i] > (compress ? (64u << 10) : (128u << 10));
         if (big) return compress ? cj::frames_compress(c, codec, where, bt, params) : cj::frames_decompress(c, codec, where, bt);
+    }
+    // a raw Snappy block larger than 128 KiB is compressed piecewise, one warp per 64 KiB (frames.cu)
+    if (codec == CJ_SNAPPY_RAW && compress && where != CJ_DEVICE && bt->n) {
+        bool big = false;
+        for (size_t i = 0; i < bt->n && !big; i++) big = bt->src_len[i] > (128u << 10) && bt->src_len[i] <= 0xFFFFFFFFull;
+        if (big) return cj::frames_compress(c, codec, where, bt, params);
     }
     // LZ4 frame decode is a per-unit kernel (one warp walks a frame's blocks), so it shares the block-codec plumbing
     if (codec != CJ_SNAPPY_RAW && codec != CJ_LZ4_BLOCK && codec != CJ_LZ4_FRAME && codec != CJ_ZSTD) { cj_set_error("unknown codec %d", codec); return CJ_E_INVALID_ARG; }

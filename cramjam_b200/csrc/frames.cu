@@ -1079,7 +1079,8 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
 // walks the frame headers; a stream of two or more frames that all declare their content size is decoded one frame
 // per warp straight into its final position.  Anything else, and any stream whose frames do not all come back
 // clean and exactly sized, goes through the whole-stream path, which owns the exact status codes.
-constexpr size_t ZS_PIECE = 512 * 1024;
+constexpr size_t ZS_PIECE = 512 * 1024;      // piece size for large inputs
+constexpr size_t ZS_PIECE_MIN = 64 * 1024;   // small inputs are cut finer (latency is one warp's time per piece): len / 64, clamped
 
 int zstd_compress_split(cj_ctx* c, int where, const cj_batch* bt, const cj_params* params) {
     const size_t n = bt->n;
@@ -1094,9 +1095,10 @@ int zstd_compress_split(cj_ctx* c, int where, const cj_batch* bt, const cj_param
     for (size_t i = 0; i < n; i++) {
         first[i] = enc.size();
         const uint64_t L = bt->src_len[i];
+        const uint64_t piece = std::min<uint64_t>(ZS_PIECE, std::max<uint64_t>(ZS_PIECE_MIN, (L / 64 + 65535) & ~(uint64_t)65535));
         uint64_t p = 0;
         do {
-            const uint64_t len = std::min<uint64_t>(ZS_PIECE, L - p);
+            const uint64_t len = std::min<uint64_t>(piece, L - p);
             const size_t cap = cj_align16(cj_compress_bound(CJ_ZSTD, (size_t)len));
             enc.add(sbase[i] + p, len, slot_acc, cap);
             slot_acc += cap;
@@ -1223,6 +1225,95 @@ int zstd_decompress_frames(cj_ctx* c, int where, const cj_batch* bt) {
     return rc;
 }
 
+// ---- Snappy raw compress of one large buffer ----------------------------------------------------
+// A raw Snappy block is one element stream under one length preamble, and the block encoder is one warp per block.
+// snap itself matches inside 64 KiB sub-blocks with a fresh table each, so a large input is cut the same way here:
+// every 64 KiB piece is compressed as its own block by its own warp, the pieces' element streams (their own
+// preambles dropped) are spliced behind one preamble for the whole length.  Copies never cross a piece boundary,
+// so every offset stays valid.  (decompress_raw of such a block is still one warp: the element chain is serial.)
+int snappy_raw_compress_split(cj_ctx* c, int where, const cj_batch* bt) {
+    const size_t n = bt->n;
+    PhaseTrace tr(c, "snappy_raw_compress");
+    std::vector<uint64_t> sbase, dbase(n);
+    int rc;
+    if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    auto varint = [](uint64_t v, uint8_t* out) { int k = 0; do { uint8_t b = v & 0x7f; v >>= 7; if (v) b |= 0x80; out[k++] = b; } while (v); return k; };
+    const size_t slot = cj_align16(32 + 65536 + 65536 / 6);
+    Items enc;
+    std::vector<size_t> first(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        first[i] = enc.size();
+        const uint64_t L = bt->src_len[i];
+        uint64_t p = 0;
+        do {
+            const uint64_t len = std::min<uint64_t>(65536, L - p);
+            enc.add(sbase[i] + p, len, enc.size() * slot, slot);
+            p += len;
+        } while (p < L);
+    }
+    first[n] = enc.size();
+    if ((rc = c->f_dtmp.ensure(enc.size() * slot + 64))) return rc;
+    const size_t need = 2 * DescCarver::bytes_for(enc.size()) + DescCarver::bytes_for(n) + 192;
+    if ((rc = c->f_ddesc.ensure(need))) return rc;
+    if ((rc = c->f_hdesc.ensure(need))) return rc;
+    DescCarver carve{c};
+    DevItems denc;
+    if ((rc = carve.put(enc, &denc))) return rc;
+    Batch b;
+    b.n = (uint32_t)enc.size();
+    b.src_base = (const uint8_t*)c->f_dsrc.p; b.src_off = denc.so; b.src_len = denc.sl;
+    b.dst_base = (uint8_t*)c->f_dtmp.p; b.dst_off = denc.dof; b.dst_cap = denc.dc; b.dst_len = denc.dl; b.status = denc.st;
+    if ((rc = cj_run_device_batch(c, CJ_SNAPPY_RAW, true, b, nullptr))) return rc;
+    if ((rc = fetch_results(c, denc))) return rc;
+    tr.mark("pieces encoded");
+    const uint64_t* dl = denc.h + 4 * denc.n;
+    const int32_t* st = (const int32_t*)(denc.h + 5 * denc.n);
+    Items mv, hdr;
+    std::vector<uint8_t> hb;
+    size_t dacc = 0;
+    for (size_t i = 0; i < n; i++) {
+        dbase[i] = dacc;
+        bt->status[i] = CJ_OK;
+        uint8_t pre[10];
+        const int pk = varint(bt->src_len[i], pre);
+        uint64_t pos = pk;
+        for (size_t k = first[i]; k < first[i + 1]; k++) {
+            if (st[k] != CJ_OK && bt->status[i] == CJ_OK) bt->status[i] = st[k];
+            uint8_t tmp[10];
+            pos += dl[k] - varint(enc.sl[k], tmp);
+        }
+        // same rule as the one-warp encoder and snap::raw::Encoder: the output must hold max_compress_len(n)
+        if (bt->status[i] == CJ_OK && bt->dst_cap[i] < cj_compress_bound(CJ_SNAPPY_RAW, (size_t)bt->src_len[i])) bt->status[i] = CJ_ST_DST_SMALL;
+        bt->dst_len[i] = bt->status[i] == CJ_OK ? pos : 0;
+        if (bt->status[i] != CJ_OK) continue;
+        hdr.add(hb.size(), pk, dacc, 0);
+        hb.insert(hb.end(), pre, pre + pk);
+        pos = pk;
+        for (size_t k = first[i]; k < first[i + 1]; k++) {
+            uint8_t tmp[10];
+            const int sk = varint(enc.sl[k], tmp);
+            mv.add(enc.dof[k] + sk, dl[k] - sk, dacc + pos, 0);
+            pos += dl[k] - sk;
+        }
+        dacc += cj_align16((size_t)pos);
+    }
+    if ((rc = c->f_ddst.ensure(dacc + hb.size() + 128))) return rc;
+    if ((rc = c->f_hdst.ensure(hb.size() + 64))) return rc;
+    memcpy(c->f_hdst.p, hb.data(), hb.size());
+    if (hb.size()) CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->f_ddst.p + dacc, c->f_hdst.p, hb.size(), cudaMemcpyHostToDevice, c->stream));
+    for (auto& v : hdr.so) v += dacc;
+    DevItems dmv, dhdr;
+    if ((rc = carve.put(mv, &dmv))) return rc;
+    if ((rc = carve.put(hdr, &dhdr))) return rc;
+    if ((rc = copy_units(c, (uint32_t)mv.size(), (const uint8_t*)c->f_dtmp.p, dmv.so, dmv.sl, (uint8_t*)c->f_ddst.p, dmv.dof))) return rc;
+    if ((rc = copy_units(c, (uint32_t)hdr.size(), (const uint8_t*)c->f_ddst.p, dhdr.so, dhdr.sl, (uint8_t*)c->f_ddst.p, dhdr.dof))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // f_hdst is reused by download_units
+    tr.mark("splice");
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
+}
+
 }  // namespace
 
 int frames_decompress(cj_ctx* c, int codec, int where, const cj_batch* bt) {
@@ -1247,6 +1338,7 @@ int frames_compress(cj_ctx* c, int codec, int where, const cj_batch* bt, const c
     if (codec == CJ_SNAPPY_FRAMED) return snappy_framed_compress(c, where, bt);
     if (codec == CJ_LZ4_FRAME) return lz4f_compress(c, where, bt, params);
     if (codec == CJ_ZSTD) return zstd_compress_split(c, where, bt, params);
+    if (codec == CJ_SNAPPY_RAW) return snappy_raw_compress_split(c, where, bt);
     cj_set_error("unknown frame codec %d", codec);
     return CJ_E_INVALID_ARG;
 }

@@ -102,3 +102,24 @@ def test_lz4_effort_knobs_round_trip_and_order():
         sizes.append(sum(len(c) for c in enc))
     assert sizes[0] >= sizes[1] >= sizes[2] >= sizes[3], sizes
     assert sizes[0] > sizes[3]
+
+
+def test_snappy_raw_large_block_is_compressed_piecewise():
+    """compress_raw of one large buffer: 64 KiB pieces on separate warps under one preamble; Google snappy (pyarrow),
+    the oracle and the decode kernel must all read it back."""
+    data = capi.synth_host(20, 65536, seed=3, first_index=77).tobytes() + b"0123456789" * 321
+    bound = capi.lib().cj_compress_bound(capi.SNAPPY_RAW, len(data))
+    enc, st = ctx().run_host_units(capi.SNAPPY_RAW, True, [data, data[:65536 * 3], b"abc"], [bound, bound, 64])
+    assert (st == 0).all()
+    assert O.snappy_raw_decompress(enc[0]) == data and O.snappy_raw_decompress(enc[1]) == data[:65536 * 3] and O.snappy_raw_decompress(enc[2]) == b"abc"
+    assert len(enc[0]) < len(data) / 1.8
+    try:
+        import pyarrow as pa
+        assert pa.decompress(enc[0], decompressed_size=len(data), codec="snappy", asbytes=True) == data
+    except ImportError:
+        pass
+    outs, st = ctx().run_host_units(capi.SNAPPY_RAW, False, enc, [len(data), 65536 * 3, 3])
+    assert (st == 0).all() and outs[0] == data
+    # too small an output is an error, never a truncation
+    _, st = ctx().run_host_units(capi.SNAPPY_RAW, True, [data], [bound - 1])
+    assert st[0] == 5
