@@ -355,6 +355,39 @@ def run_ours(args):
                 extras["zstd_ratio_libzstd_l3"] = ZF * ZU / float(zl.sum())
         except Exception as e:  # extras never fail the headline line
             extras["zstd_error"] = repr(e)[:200]
+        # the experimental generation-3 decode path (index walk + lane state machines) on the headline batch
+        try:
+            t_clen_in = i64(clen)   # the extras above reused t_clen for other codecs
+            ctx.set_decode_path(3, 4096)
+            ms_g3 = timed(lambda: ctx.decompress_batch(capi.SNAPPY_RAW, capi.DEVICE, B, comp, t_coff, t_clen_in, out, t_raw_off, t_raw_len, t_dl, t_st), k=3)
+            assert int((t_st[:B] != 0).sum()) == 0
+            extras["snappy_block_decompress_gen3_GBps"] = B * U / (ms_g3 * 1e6)
+        except Exception as e:
+            extras["gen3_error"] = repr(e)[:200]
+        finally:
+            ctx.set_decode_path(2, 4096)
+        # single-buffer calls through the cramjam-compatible Python module (BASELINE configs[0] shape and a large buffer)
+        try:
+            from cramjam_b200 import cramjam as cj_mod
+            api = {}
+            for mib in (1, 256):
+                buf = raw[: mib << 20].cpu().numpy().tobytes()
+                for name, mod in (("snappy", cj_mod.snappy), ("lz4", cj_mod.lz4), ("zstd", cj_mod.zstd)):
+                    def wall(f, reps):
+                        f()
+                        t0 = time.perf_counter()
+                        for _ in range(reps):
+                            r = f()
+                        return (time.perf_counter() - t0) / reps, r
+                    reps = 10 if mib == 1 else 2
+                    tc, cbuf = wall(lambda: mod.compress(buf), reps)
+                    cb = bytes(cbuf)
+                    td, dbuf = wall(lambda: mod.decompress(cb), reps)
+                    assert bytes(dbuf) == buf
+                    api[f"{name}_{mib}MiB"] = {"compress_ms": round(tc * 1e3, 2), "decompress_ms": round(td * 1e3, 2), "ratio": round(len(buf) / len(cb), 3)}
+            extras["api_single_buffer"] = api
+        except Exception as e:
+            extras["api_error"] = repr(e)[:200]
 
     # ---- N > 1 extra: the "batch lives on rank 0" mode — NCCL point-to-point scatter of compressed ranges,
     #      per-rank decode, gather of the outputs (north_star: NCCL only for the trivial scatter/gather) ----
