@@ -373,7 +373,8 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
     } else {
         if ((rc = c->h_src.ensure(s_bytes + 16))) return rc;
         uint8_t* stage = (uint8_t*)c->h_src.p;
-        cj_parallel_units(n, s_bytes, [&](size_t i) { memcpy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
+        if (n <= 4) { for (size_t i = 0; i < n; i++) cj_parallel_copy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); }
+        else cj_parallel_units(n, s_bytes, [&](size_t i) { memcpy(stage + so[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
         CUDA_TRY(cudaMemcpyAsync(c->d_src.p, stage, s_bytes, cudaMemcpyHostToDevice, c->stream));
     }
 
@@ -412,7 +413,8 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
         uint8_t* stage = (uint8_t*)c->h_dst.p;
         if (last_end) CUDA_TRY(cudaMemcpyAsync(stage, c->d_dst.p, last_end, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cj_parallel_units(n, last_end, [&](size_t i) { if (dl[i]) memcpy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); });
+        if (n <= 4) { for (size_t i = 0; i < n; i++) if (dl[i]) cj_parallel_copy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); }
+        else cj_parallel_units(n, last_end, [&](size_t i) { if (dl[i]) memcpy(hd + bt->dst_off[i], stage + doff[i], (size_t)dl[i]); });
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(bt->dst_len, hq + 4 * n, n * 8);

@@ -425,7 +425,8 @@ int upload_units(cj_ctx* c, const cj_batch* bt, int where, std::vector<uint64_t>
     } else {
         if ((rc = c->f_hsrc.ensure(acc + extra_tail))) return rc;
         uint8_t* stage = (uint8_t*)c->f_hsrc.p;
-        cj_parallel_units(n, acc, [&](size_t i) { memcpy(stage + base[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
+        if (n <= 4) { for (size_t i = 0; i < n; i++) cj_parallel_copy(stage + base[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); }
+        else cj_parallel_units(n, acc, [&](size_t i) { memcpy(stage + base[i], hs + bt->src_off[i], (size_t)bt->src_len[i]); });
         if (acc) CUDA_TRY(cudaMemcpyAsync(c->f_dsrc.p, stage, acc, cudaMemcpyHostToDevice, c->stream));
     }
     return CJ_OK;
@@ -446,9 +447,14 @@ int download_units(cj_ctx* c, const cj_batch* bt, int where, const std::vector<u
         if (arena_bytes) CUDA_TRY(cudaMemcpyAsync(c->f_hdst.p, c->f_ddst.p, arena_bytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const uint8_t* stage = (const uint8_t*)c->f_hdst.p;
-        cj_parallel_units(n, arena_bytes, [&](size_t i) {
-            if (bt->status[i] == CJ_OK && bt->dst_len[i]) memcpy(hd + bt->dst_off[i], stage + dbase[i], (size_t)bt->dst_len[i]);
-        });
+        if (n <= 4) {
+            for (size_t i = 0; i < n; i++)
+                if (bt->status[i] == CJ_OK && bt->dst_len[i]) cj_parallel_copy(hd + bt->dst_off[i], stage + dbase[i], (size_t)bt->dst_len[i]);
+        } else {
+            cj_parallel_units(n, arena_bytes, [&](size_t i) {
+                if (bt->status[i] == CJ_OK && bt->dst_len[i]) memcpy(hd + bt->dst_off[i], stage + dbase[i], (size_t)bt->dst_len[i]);
+            });
+        }
     }
     return CJ_OK;
 }
@@ -548,7 +554,9 @@ int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         if (bt->status[i] == CJ_OK) dacc += cj_align16((size_t)total[i]);
     }
     int rc;
+    tr.mark("host walk");
     if ((rc = upload_units(c, bt, where, sbase))) return rc;
+    tr.mark("upload");
     if ((rc = c->f_ddst.ensure(dacc + 64))) return rc;
     Items comp, stored, all;
     std::vector<uint32_t> want_crc, owner;      // per entry of `all`
@@ -596,6 +604,7 @@ int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
     if ((rc = launch_crc(c, (uint32_t)all.size(), (const uint8_t*)c->f_ddst.p, dall.so, dall.sl, dall.aux))) return rc;
     if ((rc = fetch_results(c, dcomp))) return rc;
     if ((rc = fetch_results(c, dall))) return rc;
+    tr.mark("decode + crc");
     // fold chunk results into unit results (first failure in stream order wins)
     {
         const uint64_t* cdl = dcomp.h + 4 * dcomp.n;
@@ -619,7 +628,10 @@ int snappy_framed_decompress(cj_ctx* c, int where, const cj_batch* bt) {
                 bt->dst_len[i] = ust[i] == CJ_OK ? total[i] : 0;
             }
     }
-    return download_units(c, bt, where, dbase, dacc);
+    tr.mark("fold");
+    rc = download_units(c, bt, where, dbase, dacc);
+    tr.mark("download");
+    return rc;
 }
 
 int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {

@@ -137,6 +137,22 @@ int cj_run_device_batch(cj_ctx* c, int codec, bool compress, const cj::Batch& b,
 
 static inline size_t cj_align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// memcpy of one large range on several host threads (first-touch page faults of a fresh 256 MiB output cost ~130 ms on one
+// thread; they scale with threads).
+static inline void cj_parallel_copy(void* dst, const void* src, size_t bytes) {
+    const size_t CH = (size_t)8 << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = bytes < 4 * CH ? 1 : std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, bytes / CH});
+    if (nt <= 1) { if (bytes) memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=]() {
+            const size_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+            memcpy((uint8_t*)dst + a, (const uint8_t*)src + a, b - a);
+        });
+    for (auto& t : th) t.join();
+}
+
 // Parallel loop over units on host threads (gather into / scatter out of pinned staging).
 template <class F>
 static void cj_parallel_units(size_t n, size_t bytes, F&& f) {

@@ -47,19 +47,32 @@ static cj_ctx* engine() {
     return ctx;
 }
 
+// Byte vector whose resize / sized construction leaves new bytes uninitialised: the engine overwrites the output
+// right away, and value-initialising (plus first-touching) a large output on one thread cost ~100 ms per 256 MiB —
+// the same cost the reference pays for `vec![0; len]` (src/lib.rs:217-220).  Where zeros are part of the contract
+// (a fixed-capacity output that is returned whole) they are written explicitly.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using Bytes = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 // ------------------------------------------------------------------------------------------------
 // Buffer (src/io.rs:370-684)
 // ------------------------------------------------------------------------------------------------
 class Buffer {
 public:
-    std::vector<uint8_t> own;
+    Bytes own;
     py::object view_ref;  // non-null => this Buffer is a view over another object's memory
     uint8_t* vptr = nullptr;
     size_t vlen = 0;
     size_t pos = 0;
 
     Buffer() = default;
-    explicit Buffer(std::vector<uint8_t>&& v) : own(std::move(v)) {}
+    explicit Buffer(Bytes&& v) : own(std::move(v)) {}
 
     bool is_view() const { return !view_ref.is_none() && view_ref.ptr() != nullptr; }
     uint8_t* data() { return is_view() ? vptr : own.data(); }
@@ -109,8 +122,8 @@ public:
         return (size_t)e;
     }
     size_t tell() { return (size_t)std::ftell(f); }
-    std::vector<uint8_t> read_to_end() {
-        std::vector<uint8_t> out;
+    Bytes read_to_end() {
+        Bytes out;
         const size_t total = len(), cur = tell();
         if (total > cur) {
             out.resize(total - cur);
@@ -148,7 +161,7 @@ struct Input {
     const uint8_t* p = nullptr;
     size_t n = 0;
     std::unique_ptr<PyBuf> pb;
-    std::vector<uint8_t> tmp;  // File contents (read from the current position to the end)
+    Bytes tmp;  // File contents (read from the current position to the end)
     explicit Input(py::handle h) {
         if (py::isinstance<Buffer>(h)) {
             Buffer& b = h.cast<Buffer&>();
@@ -178,7 +191,9 @@ static size_t deliver(py::handle out, const uint8_t* p, size_t n, PyObject* err_
             if (n > b.vlen - b.pos) raise(err_type, "failed to write whole buffer");
             std::memcpy(b.vptr + b.pos, p, n);
         } else {
-            if (b.pos + n > b.own.size()) b.own.resize(b.pos + n);
+            const size_t old = b.own.size();
+            if (b.pos + n > old) b.own.resize(b.pos + n);
+            if (b.pos > old) std::memset(b.own.data() + old, 0, b.pos - old);  // a write past the end zero-fills the gap (Cursor<Vec<u8>>)
             if (n) std::memcpy(b.own.data() + b.pos, p, n);
         }
         b.pos += n;
@@ -201,8 +216,8 @@ static size_t output_capacity(py::handle out) {  // only meaningful for fixed-ca
 }
 
 // ---- codec calls (GIL released, like py.allow_threads in generic!) ----
-static std::vector<uint8_t> do_compress(cj_codec codec, const uint8_t* p, size_t n, int level = -1, int accel = 1) {
-    std::vector<uint8_t> out(cj_compress_bound(codec, n));
+static Bytes do_compress(cj_codec codec, const uint8_t* p, size_t n, int level = -1, int accel = 1) {
+    Bytes out(cj_compress_bound(codec, n));
     size_t written = 0;
     cj_params prm{level, accel, 0};
     int rc;
@@ -219,7 +234,7 @@ static std::vector<uint8_t> do_compress(cj_codec codec, const uint8_t* p, size_t
 
 // cap == SIZE_MAX: size the output from the stream's own headers and shrink to what was produced;
 // otherwise exactly `cap` bytes are allocated and kept (the reference does not truncate, benchmarks/README.md:24-28).
-static std::vector<uint8_t> do_decompress(cj_codec codec, const uint8_t* p, size_t n, size_t cap, size_t* produced = nullptr) {
+static Bytes do_decompress(cj_codec codec, const uint8_t* p, size_t n, size_t cap, size_t* produced = nullptr) {
     bool shrink = false;
     int rc;
     std::string msg;
@@ -230,7 +245,7 @@ static std::vector<uint8_t> do_decompress(cj_codec codec, const uint8_t* p, size
         cap = b;
         shrink = true;
     }
-    std::vector<uint8_t> out(cap);
+    Bytes out(cap);
     size_t written = 0;
     {
         py::gil_scoped_release rel;
@@ -239,13 +254,14 @@ static std::vector<uint8_t> do_decompress(cj_codec codec, const uint8_t* p, size
     }
     if (rc) raise(g_decompression_error, msg);
     if (shrink) out.resize(written);
+    else if (written < out.size()) std::memset(out.data() + written, 0, out.size() - written);  // `vec![0; n]` returned whole
     if (produced) *produced = written;
     return out;
 }
 
 static size_t opt_size(const py::object& o) { return o.is_none() ? SIZE_MAX : o.cast<size_t>(); }
 
-static py::object make_buffer(std::vector<uint8_t> v) { return py::cast(new Buffer(std::move(v)), py::return_value_policy::take_ownership); }
+static py::object make_buffer(Bytes v) { return py::cast(new Buffer(std::move(v)), py::return_value_policy::take_ownership); }
 
 // ---- the generic compress / decompress / *_into quartet shared by the three variants ----
 static py::object generic_compress(cj_codec codec, py::handle data, int level) {
@@ -258,14 +274,14 @@ static py::object generic_decompress(cj_codec codec, py::handle data, const py::
 }
 static size_t generic_compress_into(cj_codec codec, py::handle input, py::handle output, int level) {
     Input in(input);
-    std::vector<uint8_t> c = do_compress(codec, in.p, in.n, level);
+    Bytes c = do_compress(codec, in.p, in.n, level);
     return deliver(output, c.data(), c.size(), g_compression_error);
 }
 static size_t generic_decompress_into(cj_codec codec, py::handle input, py::handle output) {
     Input in(input);
     const size_t cap = output_capacity(output);
     size_t produced = 0;
-    std::vector<uint8_t> d;
+    Bytes d;
     if (cap == SIZE_MAX) {
         d = do_decompress(codec, in.p, in.n, SIZE_MAX, &produced);
     } else {
@@ -280,7 +296,7 @@ class Compressor {
 public:
     cj_codec codec;
     int level;
-    std::vector<uint8_t> pending;
+    Bytes pending;
     bool finished = false;
     Compressor(cj_codec c, int lvl) : codec(c), level(lvl) {}
     size_t compress(py::handle input) {
@@ -291,7 +307,7 @@ public:
     }
     bool emitted_any = false;
     py::object emit() {  // a complete stream / frame per call; concatenated streams are legal in all three formats
-        std::vector<uint8_t> out = do_compress(codec, pending.data(), pending.size(), level);
+        Bytes out = do_compress(codec, pending.data(), pending.size(), level);
         pending.clear();
         emitted_any = true;
         return make_buffer(std::move(out));
@@ -311,27 +327,27 @@ public:
 class Decompressor {
 public:
     cj_codec codec;
-    std::vector<uint8_t> acc;
+    Bytes acc;
     bool finished = false;
     explicit Decompressor(cj_codec c) : codec(c) {}
     void check() const { if (finished) raise(g_decompression_error, "Appears `finish()` was called on this instance"); }
     size_t decompress(py::handle input) {
         check();
         Input in(input);
-        std::vector<uint8_t> d = do_decompress(codec, in.p, in.n, SIZE_MAX);
+        Bytes d = do_decompress(codec, in.p, in.n, SIZE_MAX);
         acc.insert(acc.end(), d.begin(), d.end());
         return d.size();
     }
     py::object flush() {
         check();
-        std::vector<uint8_t> out;
+        Bytes out;
         out.swap(acc);
         return make_buffer(std::move(out));
     }
     py::object finish() {
         check();
         finished = true;
-        std::vector<uint8_t> out;
+        Bytes out;
         out.swap(acc);
         return make_buffer(std::move(out));
     }
@@ -371,10 +387,10 @@ static void add_stream_classes(M& m, cj_codec codec, int kind, int default_level
 
 // ---- lz4 block helpers (src/lz4.rs:78-229) ----
 // `compression=Some(n)` is CompressionMode::HIGHCOMPRESSION(n) in the reference (src/lz4.rs:113-131): passed as the level
-static std::vector<uint8_t> lz4_block_compress(const uint8_t* p, size_t n, bool store_size, int accel, int compression = -1) {
-    std::vector<uint8_t> c = do_compress(CJ_LZ4_BLOCK, p, n, compression >= 0 ? std::max(compression, 3) : -1, accel);
+static Bytes lz4_block_compress(const uint8_t* p, size_t n, bool store_size, int accel, int compression = -1) {
+    Bytes c = do_compress(CJ_LZ4_BLOCK, p, n, compression >= 0 ? std::max(compression, 3) : -1, accel);
     if (!store_size) return c;
-    std::vector<uint8_t> out(c.size() + 4);
+    Bytes out(c.size() + 4);
     const uint32_t sz = (uint32_t)n;  // 4-byte little-endian uncompressed-size prefix (lz4::block, prepend_size)
     std::memcpy(out.data(), &sz, 4);
     if (!c.empty()) std::memcpy(out.data() + 4, c.data(), c.size());
@@ -537,7 +553,7 @@ PYBIND11_MODULE(cramjam, m) {
              py::arg("write") = py::none(), py::arg("truncate") = py::none(), py::arg("append") = py::none())
         .def("write", [](File& f, py::handle input) {
             if (py::isinstance<File>(input)) {
-                std::vector<uint8_t> d = input.cast<File&>().read_to_end();
+                Bytes d = input.cast<File&>().read_to_end();
                 f.write_all(d.data(), d.size());
                 return d.size();
             }
@@ -554,10 +570,10 @@ PYBIND11_MODULE(cramjam, m) {
             return in.n;
         }, py::arg("input"))
         .def("read", [](File& f, py::object n_bytes) {
-            std::vector<uint8_t> out;
+            Bytes out;
             if (n_bytes.is_none()) out = f.read_to_end();
             else {
-                out.resize(n_bytes.cast<size_t>());  // PyBytes::new_with(n): short reads leave zero padding, as in the reference
+                out.assign(n_bytes.cast<size_t>(), 0);  // PyBytes::new_with(n): short reads leave zero padding, as in the reference
                 const size_t got = std::fread(out.data(), 1, out.size(), f.f);
                 (void)got;
             }
@@ -565,7 +581,7 @@ PYBIND11_MODULE(cramjam, m) {
         }, py::arg("n_bytes") = py::none())
         .def("readinto", [](File& f, py::handle output) {
             const size_t cap = output_capacity(output);
-            std::vector<uint8_t> d;
+            Bytes d;
             if (cap == SIZE_MAX) d = f.read_to_end();
             else {
                 d.resize(cap);
@@ -613,7 +629,7 @@ PYBIND11_MODULE(cramjam, m) {
             Input in(input);
             PyBuf out(output);  // as_bytes_mut(): slice semantics
             if ((size_t)out.b.len < cj_compress_bound(CJ_SNAPPY_RAW, in.n)) raise(g_compression_error, "snappy: output buffer (size = " + std::to_string(out.b.len) + ") is smaller than required (size = " + std::to_string(cj_compress_bound(CJ_SNAPPY_RAW, in.n)) + ")");
-            std::vector<uint8_t> c = do_compress(CJ_SNAPPY_RAW, in.p, in.n);
+            Bytes c = do_compress(CJ_SNAPPY_RAW, in.p, in.n);
             std::memcpy(out.b.buf, c.data(), c.size());
             return c.size();
         }, py::arg("input"), py::arg("output"));
@@ -621,7 +637,7 @@ PYBIND11_MODULE(cramjam, m) {
             Input in(input);
             PyBuf out(output);
             size_t produced = 0;
-            std::vector<uint8_t> d = do_decompress(CJ_SNAPPY_RAW, in.p, in.n, (size_t)out.b.len, &produced);
+            Bytes d = do_decompress(CJ_SNAPPY_RAW, in.p, in.n, (size_t)out.b.len, &produced);
             if (produced) std::memcpy(out.b.buf, d.data(), produced);
             return produced;
         }, py::arg("input"), py::arg("output"));
@@ -657,7 +673,7 @@ PYBIND11_MODULE(cramjam, m) {
             Input in(data);
             std::string err;
             size_t written = 0;
-            std::vector<uint8_t> buf;
+            Bytes buf;
             bool ok;
             if (!output_len.is_none()) {  // Some(n): buf = vec![0; n]; size not prepended; the full n-byte buffer is returned
                 buf.assign(output_len.cast<size_t>(), 0);
@@ -686,7 +702,7 @@ PYBIND11_MODULE(cramjam, m) {
             }
             std::string e1, e2;
             size_t written = 0;
-            std::vector<uint8_t> tmp((size_t)out.b.len);
+            Bytes tmp((size_t)out.b.len);
             // first the caller's stated layout, then the opposite one; the first error is the one reported (src/lz4.rs:163-170)
             bool ok = lz4_block_decompress_into(in.p, in.n, tmp.data(), tmp.size(), size_stored, &written, &e1);
             if (!ok) ok = lz4_block_decompress_into(in.p, in.n, tmp.data(), tmp.size(), !size_stored, &written, &e2);
@@ -697,7 +713,7 @@ PYBIND11_MODULE(cramjam, m) {
         l.def("compress_block_into", [](py::handle data, py::handle output, py::object, py::object acceleration, py::object compression, py::object store_size) {
             Input in(data);
             PyBuf out(output);
-            std::vector<uint8_t> c = lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>(),
+            Bytes c = lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>(),
                                                         compression.is_none() ? -1 : compression.cast<int>());
             if (c.size() > (size_t)out.b.len) raise(g_compression_error, "Compression failed: output buffer is too small");
             std::memcpy(out.b.buf, c.data(), c.size());
