@@ -56,25 +56,30 @@ __device__ __forceinline__ void g3_redo(const G3& g, uint32_t u) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// plan: descriptor capacity per block, exclusive scan, counters reset (one CTA)
+// plan: descriptor capacity per block (one thread per block, coalesced), then an exclusive scan in place (one CTA)
 // ------------------------------------------------------------------------------------------------
 template <int CODEC>
-__global__ void __launch_bounds__(1024) g3_plan_kernel(Batch b, G3 g) {
-    __shared__ unsigned long long part[1024];
-    const uint32_t t = threadIdx.x;
-    if (t < 4) g.ctr[t] = 0;
-    __syncthreads();
-    const uint32_t lo = (uint32_t)((uint64_t)b.n * t / 1024), hi = (uint32_t)((uint64_t)b.n * (t + 1) / 1024);
-    auto cap_of = [&](uint32_t i) -> uint32_t {
-        const uint64_t sl = b.src_len[i], dc = b.dst_cap[i];
-        const bool ok = sl >= 1 && sl <= G3_MAX_SRC && dc <= G3_MAX_DST && (((uintptr_t)(b.src_base + b.src_off[i])) & 15u) == 0;
-        if (!ok) return 0;
+__global__ void __launch_bounds__(256) g3_caps_kernel(Batch b, G3 g) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const uint64_t sl = b.src_len[i], dc = b.dst_cap[i];
+    const bool ok = sl >= 1 && sl <= G3_MAX_SRC && dc <= G3_MAX_DST && (((uintptr_t)(b.src_base + b.src_off[i])) & 15u) == 0;
+    uint32_t cap = 0;
+    if (ok) {
         uint64_t c = sl / 2 + 2;
         if (CODEC == CJ_LZ4_BLOCK) c += (dc < sl * 255 ? dc : sl * 255) / 64;
-        return (uint32_t)((c + 31) & ~31ull) + 32;
-    };
+        cap = (uint32_t)((c + 31) & ~31ull) + 32;
+    }
+    g.desc_off[i] = cap;   // turned into an offset by the scan
+    g.count[i] = 0;
+}
+
+__global__ void __launch_bounds__(1024) g3_scan_kernel(uint32_t n, G3 g) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t lo = (uint32_t)((uint64_t)n * t / 1024), hi = (uint32_t)((uint64_t)n * (t + 1) / 1024);
     unsigned long long s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += cap_of(i);
+    for (uint32_t i = lo; i < hi; i++) s += g.desc_off[i];
     part[t] = s;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -87,14 +92,13 @@ __global__ void __launch_bounds__(1024) g3_plan_kernel(Batch b, G3 g) {
     const unsigned long long tot = part[1023];
     const bool fits = tot < 0xFFFF0000ull;
     for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t c = fits ? cap_of(i) : 0;
+        const uint32_t c = fits ? g.desc_off[i] : 0;
         g.desc_off[i] = (uint32_t)acc;
-        if (c == 0) g3_redo(g, i);
-        else g.count[i] = 0;
+        if (c == 0) g3_redo(g, i);   // not eligible (or nothing fits): generation 2
         acc += c;
     }
     if (t == 1023) {
-        g.desc_off[b.n] = fits ? (uint32_t)tot : 0;
+        g.desc_off[n] = fits ? (uint32_t)tot : 0;
         *g.total = fits ? tot : 0;
     }
 }
@@ -107,7 +111,11 @@ constexpr int IX_RING = 256;     // per-lane input ring (two 128-byte chunks)
 constexpr int IX_STRIDE = 33;    // staging row stride in words (bank-conflict free both ways)
 constexpr int IX_SMEM_WARP = 32 * IX_RING + 32 * IX_STRIDE * 4;
 constexpr int IX_SMEM_CTA = IX_SMEM_WARP * IX_WARPS + 1024;  // + the 256-entry tag table
-constexpr uint32_t IX_DELAY = 8;  // a chunk is read no earlier than this many iterations after its cp.async
+#ifndef CJ_G3_UNROLL
+#define CJ_G3_UNROLL 4
+#endif
+constexpr int IX_UNROLL = CJ_G3_UNROLL;   // plain elements a lane may index per iteration (amortises the per-iteration plumbing)
+constexpr uint32_t IX_DELAY = 4;  // a chunk is read no earlier than this many iterations after its cp.async
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
@@ -205,27 +213,42 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
             const uint32_t limit = iter >= ready_new ? loaded : loaded - 128;
             const bool can_read = reading && iter >= ready_old && ip + 8 <= limit;
 
-            uint32_t dtop = 0, ipd = ip, opd = op;
-            bool emit = false, fin = false, fail = false;
+            bool emitted = false, rowfull = false, fin = false, fail = false;
+            // one descriptor into this lane's staging row; a full row ends the lane's work for this iteration
+            auto put_desc = [&](uint32_t dtop, uint32_t ipd, uint32_t opd) {
+                const uint32_t k = e & 31;
+                if (k == 0) {
+                    row_ip = ipd; row_op = opd;
+                    g.rowbase[(doff + e) >> 5] = make_uint2(ipd, opd);
+                }
+                const uint32_t dip = ipd - row_ip, dop = opd - row_op;
+                if (CODEC != CJ_SNAPPY_RAW && (dip > 4095 || dop > 4095)) { fail = true; return; }  // Snappy: <= 31 x 65 by construction
+                sts32(stage + k * 4, dtop | (dip << 12) | dop);
+                e++;
+                emitted = true;
+                rowfull = (e & 31) == 0;
+            };
             if (CODEC == CJ_SNAPPY_RAW) {
-                // ---- hot path: one plain element per lane, table-driven ----
-                uint32_t ent = 0x80000000u;
-                if (can_read) {
-                    const uint32_t tag = ip < n16 ? lds8(ring + (ip & (IX_RING - 1))) : ldg_u8(src + ip);
-                    ent = lds32(lut + 4 * tag);
-                    if (!(ent >> 31)) {
+                // ---- hot path: up to IX_UNROLL plain elements per lane and iteration, table-driven ----
+                bool stop = !(reading && iter >= ready_old);
+#pragma unroll
+                for (int u = 0; u < IX_UNROLL; u++) {
+                    if (!stop && !rowfull && ip < n && ip + 8 <= limit) {
+                        const uint32_t tag = ip < n16 ? lds8(ring + (ip & (IX_RING - 1))) : ldg_u8(src + ip);
+                        const uint32_t ent = lds32(lut + 4 * tag);
                         const uint32_t adv = ent & 0x7F, len = (ent >> 8) & 0x7F;
-                        if (adv > n - ip || len > ulen - op) fail = true;
+                        if (ent >> 31) stop = true;   // literal with length bytes / 4-byte-offset copy: the rare path below
+                        else if (adv > n - ip || len > ulen - op) { fail = true; stop = true; }
                         else {
-                            dtop = (ent << 8) & 0xFF000000u; ipd = ip + 1; emit = true;
+                            put_desc((ent << 8) & 0xFF000000u, ip + 1, op);
                             ip += adv; op += len;
                         }
                     }
                 }
-                if (active && !emit && !fail) {  // rare states
+                if (active && !emitted && !fail) {  // rare states (a lane that made progress above comes back next iteration)
                     if (litrem) {
                         const uint32_t len = min(litrem, 60u);
-                        dtop = mk_desc(K_LIT, len - 1); emit = true;
+                        put_desc(mk_desc(K_LIT, len - 1), ip, op);
                         ip += len; op += len; litrem -= len;
                     } else if (ip >= n) {
                         fin = true;
@@ -298,29 +321,16 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
                     if (!fail) {  // describe one chunk of the current sequence (also in the iteration that parsed it)
                         if (litrem) {
                             const uint32_t len = min(litrem, 64u);
-                            dtop = mk_desc(K_LIT, len - 1); ipd = ip; opd = op; emit = true;
+                            put_desc(mk_desc(K_LIT, len - 1), ip, op);
                             ip += len; op += len; litrem -= len;
                         } else if (mrem) {
                             const uint32_t len = min(mrem, 64u);
-                            dtop = mk_desc(K_M16, len - 1); ipd = mip; opd = op; emit = true;
+                            put_desc(mk_desc(K_M16, len - 1), mip, op);
                             op += len; mrem -= len;
                             if (mrem == 0) ip = nextp;
                         }
                         if (lz_last && litrem == 0) fin = true;
                     }
-                }
-            }
-            if (emit) {
-                const uint32_t k = e & 31;
-                if (k == 0) {
-                    row_ip = ipd; row_op = opd;
-                    g.rowbase[(doff + e) >> 5] = make_uint2(ipd, opd);
-                }
-                const uint32_t dip = ipd - row_ip, dop = opd - row_op;
-                if (CODEC != CJ_SNAPPY_RAW && (dip > 4095 || dop > 4095)) fail = true;  // Snappy: <= 31 x 65 by construction
-                else {
-                    sts32(stage + k * 4, dtop | (dip << 12) | dop);
-                    e++;
                 }
             }
             if (fail) {
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
                 fin = false;
             }
             // ---- rows leave the staging area: full rows, and the partial last row of a finished block ----
-            const bool flushrow = active && ((emit && (e & 31) == 0) || (fin && (e & 31) != 0));
+            const bool flushrow = active && (rowfull || (fin && (e & 31) != 0));
             uint32_t fm = __ballot_sync(FULL, flushrow);
             if (fm) {
                 const uint32_t rcount = (e & 31) ? (e & 31) : 32;
@@ -361,13 +371,13 @@ __global__ void __launch_bounds__(IX_WARPS * 32, 4) g3_index_kernel(Batch b, G3 
 // kernel 2: execute, one warp per block, dynamic lane state machine
 // ------------------------------------------------------------------------------------------------
 #ifndef CJ_G3_LOG_OR
-#define CJ_G3_LOG_OR 12
+#define CJ_G3_LOG_OR 11
 #endif
 #ifndef CJ_G3_CH
-#define CJ_G3_CH 4
+#define CJ_G3_CH 8
 #endif
 #ifndef CJ_G3_CTAS
-#define CJ_G3_CTAS 5
+#define CJ_G3_CTAS 7
 #endif
 constexpr int X_LOG_OR = CJ_G3_LOG_OR;
 constexpr uint32_t X_OR = 1u << X_LOG_OR;          // output ring entries (16 bit each)
@@ -684,8 +694,11 @@ static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaSt
     g.ctr = w; w += 4;
     g.total = (unsigned long long*)w;
     g.desc = nullptr; g.rowbase = nullptr; g.arena = 0;
-    g3_plan_kernel<CODEC><<<1, 1024, 0, stream>>>(b, g);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(g.ctr, 0, 4 * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    g3_caps_kernel<CODEC><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(b, g);
+    g3_scan_kernel<<<1, 1024, 0, stream>>>((uint32_t)n, g);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     unsigned long long total = 0;
     if ((e = cudaMemcpyAsync(&total, g.total, sizeof total, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;

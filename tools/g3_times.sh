@@ -9,7 +9,7 @@ for l in open("gpurun_out/g3_bench.log"):
     if l.startswith("{"):
         d=json.loads(l); print("bench value", round(d["value"],1), "GB/s  ms/step", round(d["ms_per_step"],3), " frac", round(d["roofline"]["frac"],4))
 PY
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"g3_|lz_decode" -s 4 -c 8 --csv --log-file gpurun_out/g3_launches.csv python bench.py --no-extras --steps 2 --warmup 1 --blocks $N > gpurun_out/g3_q.log 2>&1
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"g3_|lz_decode" -s 5 -c 10 --csv --log-file gpurun_out/g3_launches.csv python bench.py --no-extras --steps 2 --warmup 1 --blocks $N > gpurun_out/g3_q.log 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open("gpurun_out/g3_launches.csv")) if len(r)>5]
