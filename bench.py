@@ -273,6 +273,10 @@ def run_ours(args):
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     clocks = sampler.stop(wall0, wall1) if sampler else None
     total_blocks = B * world
+    gen, min_units = ctx.decode_path()
+    kernel_name = ("g4_kernel<snappy> (thread per block) || lz_decode_kernel<snappy, lane-parallel> (warp per block), co-scheduled halves of one batch"
+                   if gen == 5 and B >= min_units else
+                   {3: "g3_index_kernel + g3_exec_kernel<snappy>", 4: "g4_kernel<snappy>"}.get(gen if B >= min_units else 2, "lz_decode_kernel<snappy, lane-parallel>"))
     value = total_blocks * U / (ms_dev * 1e6)
     alg_bytes = float(clen.sum()) + float(B) * U   # per launch on this rank: compressed read + uncompressed written
     peak, peak_src = peaks()
@@ -355,17 +359,20 @@ def run_ours(args):
                 extras["zstd_ratio_libzstd_l3"] = ZF * ZU / float(zl.sum())
         except Exception as e:  # extras never fail the headline line
             extras["zstd_error"] = repr(e)[:200]
-        # the experimental generation-3 decode path (index walk + lane state machines) on the headline batch
+        # the other block-decode paths on the headline batch: warp per block, index walk + lane
+        # state machines, thread per block; the headline `value` is the default path (4 and 2 side by side on a split batch)
+        default_path = ctx.decode_path()
         try:
             t_clen_in = i64(clen)   # the extras above reused t_clen for other codecs
-            ctx.set_decode_path(3, 4096)
-            ms_g3 = timed(lambda: ctx.decompress_batch(capi.SNAPPY_RAW, capi.DEVICE, B, comp, t_coff, t_clen_in, out, t_raw_off, t_raw_len, t_dl, t_st), k=3)
-            assert int((t_st[:B] != 0).sum()) == 0
-            extras["snappy_block_decompress_gen3_GBps"] = B * U / (ms_g3 * 1e6)
+            for gen, key in ((2, "snappy_block_decompress_gen2_GBps"), (3, "snappy_block_decompress_gen3_GBps"), (4, "snappy_block_decompress_gen4_GBps")):
+                ctx.set_decode_path(gen, 4096)
+                ms_g = timed(lambda: ctx.decompress_batch(capi.SNAPPY_RAW, capi.DEVICE, B, comp, t_coff, t_clen_in, out, t_raw_off, t_raw_len, t_dl, t_st), k=3)
+                assert int((t_st[:B] != 0).sum()) == 0
+                extras[key] = B * U / (ms_g * 1e6)
         except Exception as e:
-            extras["gen3_error"] = repr(e)[:200]
+            extras["decode_paths_error"] = repr(e)[:200]
         finally:
-            ctx.set_decode_path(2, 4096)
+            ctx.set_decode_path(*default_path)
         # single-buffer calls through the cramjam-compatible Python module (BASELINE configs[0] shape and a large buffer)
         try:
             from cramjam_b200 import cramjam as cj_mod
@@ -451,7 +458,7 @@ def run_ours(args):
                        "sharding": "contiguous global block ranges per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(B), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "lz_decode_kernel<snappy, lane-parallel>"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": kernel_name},
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                     "steps": e2e_steps, "path": "cj_decompress_batch(CJ_SNAPPY_RAW, CJ_PINNED) from pinned host arenas"},
             "gpu_launches": int(launches),

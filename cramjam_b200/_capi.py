@@ -58,6 +58,7 @@ def lib():
         "cj_status_string": ([i32], C.c_char_p),
         "cj_ctx_launch_count": ([vp], u64),
         "cj_ctx_set_decode_path": ([vp, C.c_int, C.c_long], C.c_int),
+        "cj_ctx_get_decode_path": ([vp, C.POINTER(C.c_int), C.POINTER(C.c_long)], C.c_int),
         "cj_ctx_last_kernel_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "cj_compress_bound": ([C.c_int, sz], sz),
         "cj_decompressed_len": ([C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
@@ -141,9 +142,15 @@ class Context:
     def synchronize(self):
         _check(lib().cj_ctx_synchronize(self._h))
 
-    def set_decode_path(self, generation, min_units=4096):
-        """LZ4 / Snappy block decode kernels: 2 = one warp per block (default), 3 = index walk + lane state machines."""
+    def set_decode_path(self, generation, min_units=32768):
+        """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 3 = index walk + lane
+        state machines, 4 = one thread per block (Snappy), 5 = 4 and 2 side by side on a split Snappy batch (default)."""
         _check(lib().cj_ctx_set_decode_path(self._h, generation, min_units))
+
+    def decode_path(self):
+        g, m = C.c_int(), C.c_long()
+        _check(lib().cj_ctx_get_decode_path(self._h, C.byref(g), C.byref(m)))
+        return g.value, m.value
 
     @property
     def launch_count(self):

@@ -70,6 +70,7 @@ int cj_ctx_create(int device, cj_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("CJ_DECODE_GEN")) c->decode_gen = atoi(v);
     if (const char* v = getenv("CJ_G3_MIN_UNITS")) c->g3_min_units = atol(v);
+    if (const char* v = getenv("CJ_G4_SHARE")) c->g4_share = std::min(100, std::max(0, atoi(v)));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUDA_TRY(cudaMalloc(&c->counters, 64 * sizeof(unsigned)));
@@ -87,6 +88,9 @@ void cj_ctx_destroy(cj_ctx* c) {
     if (c->counters) cudaFree(c->counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int i = 0; i < cj_ctx::PIPE; i++) {
@@ -114,10 +118,17 @@ int cj_ctx_synchronize(cj_ctx* c) {
 uint64_t cj_ctx_launch_count(const cj_ctx* c) { return c ? c->launches : 0; }
 
 int cj_ctx_set_decode_path(cj_ctx* c, int generation, long min_units) {
-    if (!c || (generation != 2 && generation != 3) || min_units < 1) return CJ_E_INVALID_ARG;
+    if (!c || (generation < 2 || generation > 5) || min_units < 1) return CJ_E_INVALID_ARG;
     std::lock_guard<std::mutex> g(c->mu);
     c->decode_gen = generation;
     c->g3_min_units = min_units;
+    return CJ_OK;
+}
+
+int cj_ctx_get_decode_path(const cj_ctx* c, int* generation, long* min_units) {
+    if (!c) return CJ_E_INVALID_ARG;
+    if (generation) *generation = c->decode_gen;
+    if (min_units) *min_units = c->g3_min_units;
     return CJ_OK;
 }
 
@@ -138,9 +149,9 @@ size_t cj_compress_bound(cj_codec codec, size_t n) {
     case CJ_LZ4_BLOCK: return n > 0x7E000000u ? 0 : n + n / 255 + 16;
     case CJ_SNAPPY_FRAMED: {
         size_t chunks = (n + 65535) / 65536;
-        return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16;
+        return 10 + chunks * (8 + 32 + 65536 + 65536 / 6) + 16 + 64 * 8;   // + headers of the finer chunks of small inputs (frames.cu frame_piece)
     }
-    case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8;
+    case CJ_LZ4_FRAME: return 19 + (n / 65536 + 1) * (4 + 65536 + 4) + 8 + 64 * 4;   // likewise: up to 64 blocks below 4 MiB
     // a block that does not shrink is stored raw: header + 3 bytes per block; inputs above 64 KiB are written as several
     // frames of >= 64 KiB each (frames.cu zstd_compress_split): one more frame header + block header per piece
     case CJ_ZSTD: return n + 3 * (n / (128 * 1024) + 1) + 18 + (n / 65536) * 24;
@@ -158,8 +169,32 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
-            // Generation 3 (lz_decode3.cu) is opt-in: cj_ctx_set_decode_path() or CJ_DECODE_GEN=3; see DESIGN.md §4.6 for why it is not the default.
-            if (c->decode_gen >= 3 && reset_counter && (long)b.n >= c->g3_min_units) {
+            // Large Snappy batches take the co-scheduled split (5); generations 3 and 4 alone are opt-in through
+            // cj_ctx_set_decode_path() / CJ_DECODE_GEN, everything else is generation 2.
+            if (c->decode_gen == 5 && codec == CJ_SNAPPY_RAW && reset_counter && (long)b.n >= c->g3_min_units && b.n >= 256) {
+                // Co-scheduled split: the thread-per-block kernel (bound by DRAM transactions and latency, ~1/3 of the issue slots)
+                // and the warp-per-block kernel (bound by issue slots, little DRAM traffic) run side by side on the same SMs.
+                if (!c->s_aux) {
+                    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+                    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+                    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+                }
+                const uint32_t n4 = (uint32_t)((uint64_t)b.n * (uint64_t)c->g4_share / 100) & ~63u;
+                cj::Batch b4 = b, b2 = b;
+                b4.n = n4;
+                b2.n = b.n - n4;
+                b2.src_off += n4; b2.src_len += n4; b2.dst_off += n4; b2.dst_cap += n4; b2.dst_len += n4; b2.status += n4;
+                CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+                CUDA_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+                e = n4 ? cj::launch_lz_decode4(codec, b4, c->g3, c->sm_count, c->stream) : cudaSuccess;
+                if (e == cudaSuccess && b2.n) e = cj::launch_lz_decode(codec, b2, c->counters + 63, c->sm_count, c->s_aux, true);
+                CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
+                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+                c->launches += 2;   // thread-per-block kernel + its redo list + the warp-per-block kernel
+            } else if (c->decode_gen == 4 && codec == CJ_SNAPPY_RAW && reset_counter && (long)b.n >= c->g3_min_units) {
+                e = cj::launch_lz_decode4(codec, b, c->g3, c->sm_count, c->stream);
+                c->launches += 1;
+            } else if (c->decode_gen == 3 && reset_counter && (long)b.n >= c->g3_min_units) {
                 e = cj::launch_lz_decode3(codec, b, c->g3, c->sm_count, c->stream);
                 c->launches += 3;
             } else {

@@ -365,6 +365,15 @@ inline uint32_t h_rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return 
 inline void h_wr32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
 inline uint32_t h_xxh32(const uint8_t* p, size_t n) { return xxh32_generic([&](uint64_t q) { return p[q]; }, n, 0); }
 
+// Chunk / block size of the snappy-framed and LZ4-frame encoders.  Both formats allow chunks smaller than 64 KiB; one warp
+// needs ~4 ms to compress (1 ms to decompress) 64 KiB, so a small input is cut finer to put more warps on it:
+// 64 KiB from 4 MiB up, else n / 64 rounded up to 4 KiB, at least 16 KiB (1 MiB -> 64 chunks of 16 KiB).
+inline uint64_t frame_piece(uint64_t n) {
+    if (n >= ((uint64_t)4 << 20)) return 65536;
+    const uint64_t p = (n / 64 + 4095) & ~(uint64_t)4095;
+    return std::min<uint64_t>(65536, std::max<uint64_t>(16384, p));
+}
+
 // A flat list of device work items referring to one device source arena and one device destination arena.
 struct Items {
     std::vector<uint64_t> so, sl, dof, dc;
@@ -647,8 +656,9 @@ int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
     for (size_t i = 0; i < n; i++) {
         bt->status[i] = CJ_OK;
         bt->dst_len[i] = 0;
-        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536) {
-            const uint64_t L = std::min<uint64_t>(65536, bt->src_len[i] - p);
+        const uint64_t piece = frame_piece(bt->src_len[i]);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += piece) {
+            const uint64_t L = std::min<uint64_t>(piece, bt->src_len[i] - p);
             ch.add(sbase[i] + p, L, ch.size() * slot, slot);
             owner.push_back((uint32_t)i);
         }
@@ -682,7 +692,8 @@ int snappy_framed_compress(cj_ctx* c, int where, const cj_batch* bt) {
         uint64_t pos = 10;
         hdr.add(hdr_bytes.size(), 10, dacc, 0);
         hdr_bytes.insert(hdr_bytes.end(), STREAM_ID, STREAM_ID + 10);
-        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536, k++) {
+        const uint64_t piece = frame_piece(bt->src_len[i]);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += piece, k++) {
             const uint64_t L = ch.sl[k];
             if (cst[k] != CJ_OK) { bt->status[i] = cst[k]; }
             const bool use_comp = clen[k] < L - L / 8;  // snap: keep the compressed form only if it saves >= 12.5 %
@@ -749,7 +760,8 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         bt->status[i] = CJ_OK;
         bt->dst_len[i] = 0;
         whole.add(sbase[i], bt->src_len[i], 0, 0);
-        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536) ch.add(sbase[i] + p, std::min<uint64_t>(65536, bt->src_len[i] - p), ch.size() * slot, slot);
+        const uint64_t piece = frame_piece(bt->src_len[i]);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += piece) ch.add(sbase[i] + p, std::min<uint64_t>(piece, bt->src_len[i] - p), ch.size() * slot, slot);
     }
     const size_t nc = ch.size();
     if ((rc = c->f_dtmp.ensure(nc * slot + 64))) return rc;
@@ -802,7 +814,8 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         hdr.add(hb.size(), 15, dacc, 0);
         hb.insert(hb.end(), fh, fh + 15);
         uint64_t pos = 15;
-        for (uint64_t p = 0; p < bt->src_len[i]; p += 65536, k++) {
+        const uint64_t piece = frame_piece(bt->src_len[i]);
+        for (uint64_t p = 0; p < bt->src_len[i]; p += piece, k++) {
             const uint64_t L = ch.sl[k];
             if (cst[k] != CJ_OK) bt->status[i] = cst[k];
             const bool use_comp = clen[k] < L;

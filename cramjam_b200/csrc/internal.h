@@ -92,6 +92,8 @@ struct G3Debug {
 namespace cj {
 // Two-kernel decode (index walk + lane state machines) for large batches; synchronises the stream once (plan read-back).
 cudaError_t launch_lz_decode3(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream, G3Debug* dbg = nullptr);
+// One thread per block (lz_decode4.cu, Snappy raw only) + the generation-2 kernel over whatever it declines.
+cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream);
 }
 
 struct cj_ctx {
@@ -106,8 +108,12 @@ struct cj_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
-    int decode_gen = 2;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu)
-    long g3_min_units = 4096;      // smallest batch the generation-3 path takes
+    int decode_gen = 5;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu), 4 = one thread per block
+                                   // (lz_decode4.cu, Snappy), 5 = 4 and 2 side by side on a split batch (Snappy; the default for large batches)
+    long g3_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
+    int g4_share = 50;             // decode_gen 5: percentage of a Snappy batch given to the thread-per-block kernel, the rest runs concurrently on generation 2
+    cudaStream_t s_aux = nullptr;  // second stream of that split
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)

@@ -731,6 +731,24 @@ static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaSt
     return cudaSuccess;
 }
 
+// The generation-2 kernel over a redo list filled by another path (lz_decode4.cu): ctr[1] = entries, ctr[2] = work queue.
+cudaError_t launch_lz_decode_list(int codec, const Batch& b, uint32_t* redo_list, unsigned* ctr, int sm_count, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e;
+        if ((e = set_smem(lz_decode_list_kernel<CJ_SNAPPY_RAW>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
+        if ((e = set_smem(lz_decode_list_kernel<CJ_LZ4_BLOCK>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
+        attr_done = true;
+    }
+    G3 g{};
+    g.redo_list = redo_list;
+    g.ctr = ctr;
+    const int grid = (int)std::min<size_t>(((size_t)b.n + DEC_WARPS - 1) / DEC_WARPS, (size_t)sm_count * CJ_DEC_CTAS);
+    if (codec == CJ_LZ4_BLOCK) lz_decode_list_kernel<CJ_LZ4_BLOCK><<<grid, DEC_WARPS * 32, (size_t)DEC_SMEM_WARP * DEC_WARPS, stream>>>(b, g);
+    else lz_decode_list_kernel<CJ_SNAPPY_RAW><<<grid, DEC_WARPS * 32, (size_t)DEC_SMEM_WARP * DEC_WARPS, stream>>>(b, g);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lz_decode3(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream, G3Debug* dbg) {
     return codec == CJ_LZ4_BLOCK ? launch_g3<CJ_LZ4_BLOCK>(b, sc, sm_count, stream, dbg) : launch_g3<CJ_SNAPPY_RAW>(b, sc, sm_count, stream, dbg);
 }

@@ -1,0 +1,356 @@
+// lz_decode4.cu — generation-4 batch decode of Snappy raw blocks (sm_100a): one THREAD per block.
+//
+// Same reference entry point as lz_decode.cuh (snap::raw::Decoder::decompress behind cramjam.snappy.decompress_raw /
+// decompress_raw_into, src/snappy.rs:52-60,102-108).  Generations 2 and 3 spend 20-30 warp instructions per ~8-byte
+// element because a whole warp cooperates on one block; here a lane owns a block and decodes it the way a CPU does,
+// so one warp instruction advances 32 blocks.  What makes that workable on a GPU:
+//
+//   * compressed input reaches a lane through its own 256-byte shared-memory ring, filled 16 bytes at a time by the
+//     lane's own cp.async (no cooperation, no shuffles), running up to 240 bytes ahead of the read cursor;
+//   * every sub-iteration moves at most one 8-byte CHUNK of the lane's current element.  A chunk is ISSUED (its source
+//     words are loaded: literal bytes from the input ring, back-reference bytes from the block's own output in global
+//     memory) and RETIRED G4_D sub-iterations later (shift to the output alignment, append to a 16-byte register
+//     accumulator, one aligned 16-byte st.global per 16 bytes of output), so the L2/DRAM latency of a back-reference
+//     is overlapped with the following elements instead of being waited for;
+//   * back-references that reach into bytes not yet stored (offset <= 64) are read at retire time from a 128-byte
+//     per-lane mirror of the most recent output in shared memory; offsets below 8 are expanded to a periodic pattern;
+//   * both rings are interleaved across lanes in 16-byte granules, so lane-private accesses at unrelated positions
+//     fall into different banks.
+//   Anything unusual (unaligned unit, 4-byte-offset copy, malformed element, bad offset, length mismatch) puts the
+//   block on the redo list of the generation-2 kernel, which owns all error reporting: status codes stay the oracle's.
+#include "internal.h"
+#include "lz_decode.cuh"
+
+namespace cj {
+
+#ifndef CJ_G4_D
+#define CJ_G4_D 3
+#endif
+constexpr int G4_WARPS = 2;
+constexpr int G4_D = CJ_G4_D;          // sub-iterations between issue and retire of a chunk
+constexpr uint32_t G4_INB = 256;       // input ring bytes per lane
+constexpr uint32_t G4_RECB = 128;      // recent-output mirror bytes per lane
+constexpr uint32_t G4_NEAR = 64;       // back-references up to this offset are read from the mirror at retire time
+constexpr int G4_SMEM_WARP = 32 * (G4_INB + G4_RECB + 16 * G4_D);   // + one 16-byte staging slot per chunk in flight
+constexpr int G4_SMEM_CTA = G4_SMEM_WARP * G4_WARPS + 1024;   // + the 256-entry tag table
+constexpr uint32_t G4_MAX = 1u << 30;
+static_assert(8 * (G4_D - 1) + 15 + 8 <= G4_NEAR + 1, "a far back-reference must lie entirely below the stored frontier");
+
+struct G4 {
+    uint32_t* redo_list;   // units for the generation-2 kernel
+    unsigned* ctr;         // [1] redo count  [2] redo work queue
+};
+
+__device__ __forceinline__ void g4_redo(const G4& g, uint32_t u) {
+    const unsigned i = atomicAdd(&g.ctr[1], 1u);
+    g.redo_list[i] = u;
+}
+
+__device__ __forceinline__ void g4_cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void g4_cp_async8(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+// predicated forms (no branch around them)
+__device__ __forceinline__ void g4_cp_async8_if(uint32_t saddr, const void* gptr, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(saddr), "l"(gptr), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void g4_cp_async16_if(uint32_t saddr, const void* gptr, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(saddr), "l"(gptr), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void g4_sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void g4_stg128_if(void* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w), "r"(pred) : "memory");
+}
+__device__ __forceinline__ uint2 g4_lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 g4_ldg64(const void* p) {   // coherent load: re-reads output this thread stored earlier
+    uint2 v;
+    asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void g4_stg128(void* p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 8 bytes starting `shb` (0..7) bytes into the 16-byte window {a0, a1}
+__device__ __forceinline__ uint64_t g4_funnel(uint2 a0, uint2 a1, uint32_t shb) {
+    uint32_t w0 = a0.x, w1 = a0.y, w2 = a1.x;
+    if (shb & 4u) { w0 = w1; w1 = w2; w2 = a1.y; }
+    const uint32_t s = (shb & 3u) * 8;
+    const uint32_t r0 = __funnelshift_r(w0, w1, s), r1 = __funnelshift_r(w1, w2, s);
+    return ((uint64_t)r1 << 32) | r0;
+}
+
+// Snappy tag table: [6:0] compressed size of the element, [14:8] bytes it produces, [23:22] kind, [21:16] field,
+// bit 31 = not a plain element (literal with length bytes, 4-byte-offset copy).
+constexpr uint32_t G4_LIT = 0, G4_M16 = 1, G4_M1 = 2;
+constexpr uint32_t G4_CK_LIT = 1, G4_CK_NEAR = 2, G4_CK_FAR = 3;   // where a chunk's source bytes are read from when it retires
+__device__ __forceinline__ uint32_t g4_tag_entry(uint32_t tag) {
+    const uint32_t type = tag & 3, L = (tag >> 2) + 1;
+    if (type == 0) return L <= 60 ? ((1 + L) | (L << 8) | (((G4_LIT << 6) | (L - 1)) << 16)) : 0x80000000u;
+    if (type == 1) {
+        const uint32_t len = 4 + ((tag >> 2) & 7);
+        return 2 | (len << 8) | (((G4_M1 << 6) | (tag >> 5)) << 16);
+    }
+    if (type == 2) return 3 | (L << 8) | (((G4_M16 << 6) | (L - 1)) << 16);
+    return 0x80000000u;
+}
+
+template <int CODEC>
+__global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t wbase = smem_addr(smem + (size_t)warp * G4_SMEM_WARP);
+    const uint32_t inl = wbase + lane * 16;                               // granule q of this lane's input ring: inl + q * 512
+    const uint32_t recl = wbase + 32 * G4_INB + lane * 16;                // 16-byte slot q of the output mirror: recl + q * 512
+    const uint32_t stl = wbase + 32 * (G4_INB + G4_RECB) + lane * 16;     // staging slot u of a far chunk: stl + u * 512
+    const uint32_t lut = smem_addr(smem + (size_t)G4_SMEM_WARP * G4_WARPS);
+    for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(lut + 4 * t, g4_tag_entry(t));
+    __syncthreads();
+    auto in_a = [&](uint32_t x) -> uint32_t { return inl + ((x & 0xF0u) << 5) + (x & 15u); };
+    auto rec_s = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5); };             // mirror slot (16 bytes) holding output byte p
+    auto rec_a = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5) + (p & 8u); };   // its 8-byte half
+    const uint32_t nwarps = gridDim.x * G4_WARPS;
+
+    for (uint32_t first = (blockIdx.x * G4_WARPS + warp) * 32; first < b.n; first += nwarps * 32) {
+        // ---- every lane takes one block ----
+        const uint32_t cur = first + lane;
+        bool active = false;
+        const uint8_t* src = nullptr;
+        uint8_t* dst = nullptr;
+        uint32_t n = 0, ulen = 0, ip = 0;
+        if (cur < b.n) {
+            const uint64_t sl = b.src_len[cur], dcap = b.dst_cap[cur];
+            src = b.src_base + b.src_off[cur];
+            dst = b.dst_base + b.dst_off[cur];
+            bool ok = sl >= 1 && sl <= G4_MAX && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
+            if (ok) {
+                n = (uint32_t)sl;
+                uint64_t v = 0;
+                bool done = false;
+                for (int i = 0; i < 5 && ip < n; i++) {
+                    const uint32_t x = ldg_u8(src + ip++);
+                    v |= (uint64_t)(x & 0x7f) << (7 * i);
+                    if (!(x & 0x80)) { done = true; break; }
+                }
+                ok = done && v >= 1 && v <= dcap && v <= G4_MAX;
+                ulen = (uint32_t)v;
+            }
+            if (ok) active = true;
+            else g4_redo(g, cur);
+        }
+        const uint32_t n16 = n & ~15u;   // the ragged last granule is read straight from global memory
+        uint32_t loaded = 0, lim = 0;    // input granules requested / bytes known to have arrived in the ring
+        uint32_t opi = 0, opr = 0;       // output position of the next chunk to issue / to retire
+        uint32_t rem = 0, sp = 0;        // bytes of the current element still to issue; literal: input position, copy: offset
+        bool is_lit = false, fin = false;
+        uint64_t lo = 0, hi = 0;         // output bytes [opr & ~15, opr)
+        uint32_t tw0 = 0, tw1 = 0;       // the two ring words around ip, fetched one sub-iteration ahead
+        bool tw_ok = false;              // ... and whether they had arrived in the ring when they were fetched
+        uint32_t M[G4_D], P[G4_D];       // chunk in flight: M = bytes | kind << 4;  P = input position / offset / byte shift
+#pragma unroll
+        for (int u = 0; u < G4_D; u++) { M[u] = 0; P[u] = 0; }
+
+        // The loop body is written without branches on the common path (selects and predicated PTX), so that the retire
+        // chain, the tag-decode chain and the issue of the next chunk interleave inside one basic block: with one thread
+        // per block only ~3.5 warps share a scheduler, and instruction-level parallelism has to hide what they cannot.
+        while (__any_sync(FULL, active)) {
+            lim = loaded;   // granules requested one whole iteration ago have arrived (wait_group below)
+#pragma unroll
+            for (int u = 0; u < G4_D; u++) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(G4_D - 1) : "memory");
+                // Shared-memory accesses are volatile asm and keep their program order, so the loads of the two independent
+                // chains (retire, tag decode) are written first and their arithmetic afterwards.
+                // ---- [A] retire: load the source window of the chunk issued G4_D sub-iterations ago (in shared memory by now) ----
+                const uint32_t m = M[u], rc = m & 15u, rkind = m >> 4, rp_ = P[u];
+                const uint32_t rs = rkind == G4_CK_LIT ? rp_ : opr - rp_;
+                const uint32_t rs0 = rs & ~7u, rs1 = rs0 + 8;
+                const uint32_t rsa = stl + u * 512;
+                const uint32_t ra = rkind == G4_CK_LIT ? in_a(rs0) : (rkind == G4_CK_NEAR ? rec_a(rs0) : rsa);
+                const uint32_t ra2 = rkind == G4_CK_LIT ? in_a(rs1) : (rkind == G4_CK_NEAR ? rec_a(rs1) : rsa + 8);
+                const uint2 a0 = g4_lds64(ra), a1 = g4_lds64(ra2);
+                // ---- [B] tag decode: table entry of the tag fetched at the end of the previous sub-iteration ----
+                const uint32_t t = __funnelshift_r(tw0, tw1, (ip & 3u) * 8);
+                const uint32_t ent = lds32(lut + 4 * (t & 255u));
+                // ---- [C] retire: align, append to the accumulator, store ----
+                {
+                    const uint32_t shb = rkind == G4_CK_FAR ? rp_ : (rs & 7u);
+                    uint64_t v = g4_funnel(a0, a1, shb);
+                    if (rkind == G4_CK_NEAR && rp_ < 8) {   // overlapping copy: the `rp_` bytes repeat
+                        v &= ~0ull >> (64 - 8 * rp_);
+                        v |= v << (8 * rp_);
+                        if (rp_ < 4) v |= v << (16 * rp_);
+                        if (rp_ < 2) v |= v << 32;
+                    }
+                    v = rc ? v & (~0ull >> (64 - 8 * rc)) : 0ull;
+                    const uint32_t k = opr & 15u, sh = (k & 7u) * 8;
+                    const uint64_t vl = v << sh, vh = sh ? v >> (64 - sh) : 0ull;
+                    const bool lowhalf = k < 8;
+                    lo |= lowhalf ? vl : 0ull;
+                    hi |= lowhalf ? vh : vl;
+                    const uint32_t cross = k + rc >= 16 ? 1u : 0u;   // the 16-byte word is complete (only from the upper half)
+                    g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), 1u);
+                    g4_stg128_if(dst + (opr & ~15u), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), cross);
+                    lo = cross ? vh : lo;
+                    hi = cross ? 0ull : hi;
+                    opr += rc;
+                    g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), 0u, 0u, cross);   // the spilled bytes open the next mirror slot
+                }
+                // ---- [D] decode the next element if the current one is fully issued (plain tags that are in the ring) ----
+                const bool need = active && rem == 0 && !fin;
+                const bool atend = ip >= n;
+                fin = fin || (need && atend);
+                bool slow;
+                {
+                    const bool fast = need && !atend && tw_ok;
+                    const uint32_t adv = ent & 0x7Fu, len = (ent >> 8) & 0x7Fu, kind = (ent >> 22) & 3u;
+                    const uint32_t off = kind == G4_M1 ? (((ent >> 16) & 7u) << 8) | ((t >> 8) & 0xFFu) : (t >> 8) & 0xFFFFu;
+                    const bool lit = kind == G4_LIT;
+                    const bool bad = (ent >> 31) != 0 || adv > n - ip || len > ulen - opi || (!lit && (off == 0 || off > opi));
+                    const bool take = fast && !bad;
+                    slow = (fast && bad) || (need && !atend && !fast && ip + 4 > n16);   // rare tag, failed check, or the block's last bytes
+                    is_lit = take ? lit : is_lit;
+                    sp = take ? (lit ? ip + 1 : off) : sp;
+                    rem = take ? len : rem;
+                    ip = take ? ip + adv : ip;
+                }
+                // ---- issue one chunk of the current element ----
+                {
+                    uint32_t c = min(rem, 8u);
+                    const bool litok = sp + c <= lim;
+                    const bool isnear = !is_lit && sp <= G4_NEAR;
+                    const bool isfar = !is_lit && !isnear && c != 0;
+                    slow = slow || (is_lit && c != 0 && !litok && sp + c > n16);   // literal bytes that never enter the ring
+                    c = (is_lit && !litok) ? 0u : c;
+                    const uint32_t fs = opi - sp;
+                    const uint8_t* gp = dst + (fs & ~7u);
+                    g4_cp_async8_if(stl + u * 512, gp, isfar ? 1u : 0u);
+                    g4_cp_async8_if(stl + u * 512 + 8, gp + 8, isfar ? 1u : 0u);
+                    const uint32_t kind = is_lit ? G4_CK_LIT : (isnear ? G4_CK_NEAR : G4_CK_FAR);
+                    M[u] = c ? (c | (kind << 4)) : 0u;
+                    P[u] = (is_lit || isnear) ? sp : (fs & 7u);
+                    sp += is_lit ? c : 0u;
+                    opi += c;
+                    rem -= c;
+                }
+                // ---- everything unusual, at most a few times per block ----
+                if (slow) {
+                    bool fail = false;
+                    if (rem == 0) {   // tag decode from global memory, with every check
+                        uint32_t t = ldg_u8(src + ip);
+                        if (ip + 1 < n) t |= ldg_u8(src + ip + 1) << 8;
+                        if (ip + 2 < n) t |= ldg_u8(src + ip + 2) << 16;
+                        const uint32_t tag = t & 255u;
+                        const uint32_t ent = g4_tag_entry(tag);
+                        if (ent >> 31) {
+                            const uint32_t nb = (tag >> 2) - 59;
+                            if ((tag & 3u) != 0 || nb > n - ip - 1) fail = true;   // 4-byte-offset copies: generation 2
+                            else {
+                                uint32_t v = 0;
+                                for (uint32_t i = 0; i < nb; i++) v |= ldg_u8(src + ip + 1 + i) << (8 * i);
+                                const uint64_t LL = (uint64_t)v + 1;
+                                const uint32_t q = ip + 1 + nb;
+                                if (LL > n - q || LL > ulen - opi) fail = true;
+                                else { is_lit = true; sp = q; rem = (uint32_t)LL; ip = q + (uint32_t)LL; }
+                            }
+                        } else {
+                            const uint32_t adv = ent & 0x7Fu, len = (ent >> 8) & 0x7Fu, kind = (ent >> 22) & 3u;
+                            const uint32_t off = kind == G4_M1 ? (((ent >> 16) & 7u) << 8) | ((t >> 8) & 0xFFu) : (t >> 8) & 0xFFFFu;
+                            const bool lit = kind == G4_LIT;
+                            if (adv > n - ip || len > ulen - opi || (!lit && (off == 0 || off > opi))) fail = true;
+                            else { is_lit = lit; sp = lit ? ip + 1 : off; rem = len; ip += adv; }
+                        }
+                    } else {          // a literal chunk at the end of the block: staged by hand, retired like a far chunk
+                        const uint32_t c = min(rem, 8u);
+                        uint32_t x0 = 0, x1 = 0;
+                        for (uint32_t j = 0; j < c; j++) {
+                            const uint32_t bb = ldg_u8(src + sp + j);
+                            if (j < 4) x0 |= bb << (8 * j);
+                            else x1 |= bb << (8 * (j - 4));
+                        }
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(stl + u * 512), "r"(x0), "r"(x1) : "memory");
+                        M[u] = c | (G4_CK_FAR << 4);
+                        P[u] = 0;
+                        sp += c;
+                        opi += c;
+                        rem -= c;
+                    }
+                    if (fail) {
+                        g4_redo(g, cur);
+                        active = false;
+                        rem = 0;
+                        fin = true;
+                    }
+                }
+                // ---- fetch the tag words of the next element; their latency overlaps the loop bookkeeping ----
+                tw0 = lds32(in_a(ip & ~3u));
+                tw1 = lds32(in_a((ip & ~3u) + 4));
+                tw_ok = ip + 4 <= lim;
+                // ---- input ring, once per iteration: up to two more granules if they fit ahead of everything still needed ----
+                if (u == 0) {
+                    const uint32_t rp = (rem && is_lit) ? sp : ip;
+                    const uint32_t keep = (rp > 16u * G4_D ? rp - 16u * G4_D : 0u) & ~15u;   // chunks in flight read at most this far back
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const bool go = active && loaded < n16 && loaded <= keep + (G4_INB - 16);
+                        g4_cp_async16_if(inl + ((loaded & 0xF0u) << 5), src + loaded, go ? 1u : 0u);
+                        loaded += go ? 16u : 0u;
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            // ---- a lane is done when its input is consumed and every chunk has retired ----
+            if (active && fin) {
+                bool empty = true;
+#pragma unroll
+                for (int u = 0; u < G4_D; u++) empty = empty && M[u] == 0;
+                if (empty) {
+                    if (opi != ulen) g4_redo(g, cur);
+                    else {
+                        const uint32_t k = opr & 15u;
+                        uint8_t* tail = dst + (opr & ~15u);
+                        for (uint32_t j = 0; j < k; j++) tail[j] = (uint8_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))));
+                        b.dst_len[cur] = ulen;
+                        b.status[cur] = CJ_OK;
+                    }
+                    active = false;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_lz_decode_list(int codec, const Batch& b, uint32_t* redo_list, unsigned* ctr, int sm_count, cudaStream_t stream);
+
+cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(g4_kernel<CJ_SNAPPY_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_CTA);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const size_t n = b.n;
+    if (sc.ensure_fixed((n + 8) * 4 + 64) != 0) return cudaErrorMemoryAllocation;
+    G4 g;
+    g.ctr = (unsigned*)sc.fixed();
+    g.redo_list = (uint32_t*)sc.fixed() + 8;
+    cudaError_t e = cudaMemsetAsync(g.ctr, 0, 4 * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    const int per = G4_WARPS * 32;
+    const int grid = (int)std::min<size_t>((n + per - 1) / per, (size_t)sm_count * 8);
+    g4_kernel<CJ_SNAPPY_RAW><<<grid, per, (size_t)G4_SMEM_CTA, stream>>>(b, g);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return launch_lz_decode_list(codec, b, g.redo_list, g.ctr, sm_count, stream);
+}
+
+}  // namespace cj

@@ -1,5 +1,6 @@
-"""-m gpu parity tests of the generation-3 decode path (lz_decode3.cu: index walk + lane state
-machines + generation-2 redo list), forced on through cj_ctx_set_decode_path() for every batch size.
+"""-m gpu parity tests of the alternative block-decode paths — generation 3 (lz_decode3.cu: index walk + lane state
+machines), generation 4 (lz_decode4.cu: one thread per block) and 5 (4 and 2 side by side on a split batch), each with
+the generation-2 redo list — forced on through cj_ctx_set_decode_path() for every batch size.
 Same oracle, same status-code expectations as test_gpu_lz_decode.py."""
 import numpy as np
 import pytest
@@ -16,11 +17,12 @@ pytestmark = pytest.mark.gpu
 CASES = corpus.edge_cases()
 
 
-@pytest.fixture(autouse=True)
-def gen3():
-    ctx().set_decode_path(3, 1)
+@pytest.fixture(autouse=True, params=[3, 4, 5], ids=["gen3", "gen4", "gen5"])
+def gen3(request):
+    default = ctx().decode_path()
+    ctx().set_decode_path(request.param, 1)   # generations 4 and 5 take Snappy only; LZ4 batches stay on generation 2
     yield
-    ctx().set_decode_path(2, 4096)
+    ctx().set_decode_path(*default)
 
 
 @pytest.mark.parametrize("codec", [capi.SNAPPY_RAW, capi.LZ4_BLOCK])

@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: tools/g5_sweep.sh "shares"  -- bench value of the co-scheduled split (CJ_DECODE_GEN=5) for several gen-4 shares
+for s in ${1:-"25 40 50 60"}; do
+  CJ_DECODE_GEN=5 CJ_G4_SHARE=$s timeout 200 python bench.py --no-extras --steps 3 --warmup 3 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('share $s: value', round(d['value'],1), 'GB/s  ms/step', round(d['ms_per_step'],3))
+"
+done
