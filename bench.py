@@ -360,11 +360,12 @@ def run_ours(args):
         except Exception as e:  # extras never fail the headline line
             extras["zstd_error"] = repr(e)[:200]
         # the other block-decode paths on the headline batch: warp per block, index walk + lane
-        # state machines, thread per block; the headline `value` is the default path (4 and 2 side by side on a split batch)
+        # state machines, and thread-per-block and warp-per-block side by side on a split batch; the headline `value` is the
+        # default path (thread per block)
         default_path = ctx.decode_path()
         try:
             t_clen_in = i64(clen)   # the extras above reused t_clen for other codecs
-            for gen, key in ((2, "snappy_block_decompress_gen2_GBps"), (3, "snappy_block_decompress_gen3_GBps"), (4, "snappy_block_decompress_gen4_GBps")):
+            for gen, key in ((2, "snappy_block_decompress_gen2_GBps"), (3, "snappy_block_decompress_gen3_GBps"), (5, "snappy_block_decompress_gen5_GBps")):
                 ctx.set_decode_path(gen, 4096)
                 ms_g = timed(lambda: ctx.decompress_batch(capi.SNAPPY_RAW, capi.DEVICE, B, comp, t_coff, t_clen_in, out, t_raw_off, t_raw_len, t_dl, t_st), k=3)
                 assert int((t_st[:B] != 0).sum()) == 0

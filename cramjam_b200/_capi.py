@@ -144,7 +144,7 @@ class Context:
 
     def set_decode_path(self, generation, min_units=32768):
         """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 3 = index walk + lane
-        state machines, 4 = one thread per block (Snappy), 5 = 4 and 2 side by side on a split Snappy batch (default)."""
+        state machines, 4 = one thread per block (Snappy; the default), 5 = 4 and 2 side by side on a split Snappy batch."""
         _check(lib().cj_ctx_set_decode_path(self._h, generation, min_units))
 
     def decode_path(self):

@@ -169,8 +169,8 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
-            // Large Snappy batches take the co-scheduled split (5); generations 3 and 4 alone are opt-in through
-            // cj_ctx_set_decode_path() / CJ_DECODE_GEN, everything else is generation 2.
+            // Large Snappy batches take the thread-per-block kernel (4); generation 3 and the co-scheduled split (5) are opt-in
+            // through cj_ctx_set_decode_path() / CJ_DECODE_GEN, everything else is generation 2.
             if (c->decode_gen == 5 && codec == CJ_SNAPPY_RAW && reset_counter && (long)b.n >= c->g3_min_units && b.n >= 256) {
                 // Co-scheduled split: the thread-per-block kernel (bound by DRAM transactions and latency, ~1/3 of the issue slots)
                 // and the warp-per-block kernel (bound by issue slots, little DRAM traffic) run side by side on the same SMs.
@@ -191,7 +191,7 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
                 CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
                 CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
                 c->launches += 2;   // thread-per-block kernel + its redo list + the warp-per-block kernel
-            } else if (c->decode_gen == 4 && codec == CJ_SNAPPY_RAW && reset_counter && (long)b.n >= c->g3_min_units) {
+            } else if (c->decode_gen == 4 && reset_counter && (long)b.n >= c->g3_min_units) {
                 e = cj::launch_lz_decode4(codec, b, c->g3, c->sm_count, c->stream);
                 c->launches += 1;
             } else if (c->decode_gen == 3 && reset_counter && (long)b.n >= c->g3_min_units) {

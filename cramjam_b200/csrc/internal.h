@@ -108,8 +108,8 @@ struct cj_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
-    int decode_gen = 5;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu), 4 = one thread per block
-                                   // (lz_decode4.cu, Snappy), 5 = 4 and 2 side by side on a split batch (Snappy; the default for large batches)
+    int decode_gen = 4;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu), 4 = one thread per block
+                                   // (lz_decode4.cu, Snappy), the default for large batches), 5 = 4 and 2 side by side on a split batch (Snappy)
     long g3_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
     int g4_share = 50;             // decode_gen 5: percentage of a Snappy batch given to the thread-per-block kernel, the rest runs concurrently on generation 2
     cudaStream_t s_aux = nullptr;  // second stream of that split

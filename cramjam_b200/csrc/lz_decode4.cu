@@ -26,15 +26,15 @@ namespace cj {
 #ifndef CJ_G4_D
 #define CJ_G4_D 3
 #endif
-constexpr int G4_WARPS = 2;
-constexpr int G4_D = CJ_G4_D;          // sub-iterations between issue and retire of a chunk
+constexpr int G4_MAX_WARPS = 16;       // warps per CTA: chosen at launch so that one CTA per SM holds the whole batch when it fits
+constexpr int G4_DMAX = 4;             // sub-iterations between issue and retire of a chunk: template parameter D <= G4_DMAX
 constexpr uint32_t G4_INB = 256;       // input ring bytes per lane
 constexpr uint32_t G4_RECB = 128;      // recent-output mirror bytes per lane
 constexpr uint32_t G4_NEAR = 64;       // back-references up to this offset are read from the mirror at retire time
-constexpr int G4_SMEM_WARP = 32 * (G4_INB + G4_RECB + 16 * G4_D);   // + one 16-byte staging slot per chunk in flight
-constexpr int G4_SMEM_CTA = G4_SMEM_WARP * G4_WARPS + 1024;   // + the 256-entry tag table
+constexpr int g4_smem_warp(int D) { return 32 * (int)(G4_INB + G4_RECB + 16 * D); }   // + one 16-byte staging slot per chunk in flight
+constexpr int g4_smem_cta(int D, int warps) { return g4_smem_warp(D) * warps + 1024; }   // + the 256-entry tag table
 constexpr uint32_t G4_MAX = 1u << 30;
-static_assert(8 * (G4_D - 1) + 15 + 8 <= G4_NEAR + 1, "a far back-reference must lie entirely below the stored frontier");
+static_assert(8 * (G4_DMAX - 1) + 15 + 8 <= G4_NEAR + 1, "a far back-reference must lie entirely below the stored frontier");
 
 struct G4 {
     uint32_t* redo_list;   // units for the generation-2 kernel
@@ -103,8 +103,10 @@ __device__ __forceinline__ uint32_t g4_tag_entry(uint32_t tag) {
     return 0x80000000u;
 }
 
-template <int CODEC>
-__global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
+template <int CODEC, int G4_D>
+__global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g) {
+    constexpr int G4_SMEM_WARP = g4_smem_warp(G4_D);
+    const int G4_WARPS = blockDim.x >> 5;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -113,8 +115,10 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
     const uint32_t recl = wbase + 32 * G4_INB + lane * 16;                // 16-byte slot q of the output mirror: recl + q * 512
     const uint32_t stl = wbase + 32 * (G4_INB + G4_RECB) + lane * 16;     // staging slot u of a far chunk: stl + u * 512
     const uint32_t lut = smem_addr(smem + (size_t)G4_SMEM_WARP * G4_WARPS);
-    for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(lut + 4 * t, g4_tag_entry(t));
-    __syncthreads();
+    if (CODEC == CJ_SNAPPY_RAW) {
+        for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(lut + 4 * t, g4_tag_entry(t));
+        __syncthreads();
+    }
     auto in_a = [&](uint32_t x) -> uint32_t { return inl + ((x & 0xF0u) << 5) + (x & 15u); };
     auto rec_s = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5); };             // mirror slot (16 bytes) holding output byte p
     auto rec_a = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5) + (p & 8u); };   // its 8-byte half
@@ -134,15 +138,20 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
             bool ok = sl >= 1 && sl <= G4_MAX && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
             if (ok) {
                 n = (uint32_t)sl;
-                uint64_t v = 0;
-                bool done = false;
-                for (int i = 0; i < 5 && ip < n; i++) {
-                    const uint32_t x = ldg_u8(src + ip++);
-                    v |= (uint64_t)(x & 0x7f) << (7 * i);
-                    if (!(x & 0x80)) { done = true; break; }
+                if constexpr (CODEC == CJ_SNAPPY_RAW) {
+                    uint64_t v = 0;
+                    bool done = false;
+                    for (int i = 0; i < 5 && ip < n; i++) {
+                        const uint32_t x = ldg_u8(src + ip++);
+                        v |= (uint64_t)(x & 0x7f) << (7 * i);
+                        if (!(x & 0x80)) { done = true; break; }
+                    }
+                    ok = done && v >= 1 && v <= dcap && v <= G4_MAX;
+                    ulen = (uint32_t)v;
+                } else {
+                    ok = dcap >= 1 && dcap <= G4_MAX;
+                    ulen = (uint32_t)dcap;   // LZ4: the capacity; LZ4_decompress_safe's rules are applied against it
                 }
-                ok = done && v >= 1 && v <= dcap && v <= G4_MAX;
-                ulen = (uint32_t)v;
             }
             if (ok) active = true;
             else g4_redo(g, cur);
@@ -152,6 +161,8 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
         uint32_t opi = 0, opr = 0;       // output position of the next chunk to issue / to retire
         uint32_t rem = 0, sp = 0;        // bytes of the current element still to issue; literal: input position, copy: offset
         bool is_lit = false, fin = false;
+        bool lz_phase = false, lz_last = false;   // LZ4: the next thing to decode is an offset (not a token); the final sequence has been seen
+        uint32_t lz_ml = 0;                       // LZ4: match-length nibble of the token whose literals are being issued
         uint64_t lo = 0, hi = 0;         // output bytes [opr & ~15, opr)
         uint32_t tw0 = 0, tw1 = 0;       // the two ring words around ip, fetched one sub-iteration ahead
         bool tw_ok = false;              // ... and whether they had arrived in the ring when they were fetched
@@ -179,7 +190,8 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
                 const uint2 a0 = g4_lds64(ra), a1 = g4_lds64(ra2);
                 // ---- [B] tag decode: table entry of the tag fetched at the end of the previous sub-iteration ----
                 const uint32_t t = __funnelshift_r(tw0, tw1, (ip & 3u) * 8);
-                const uint32_t ent = lds32(lut + 4 * (t & 255u));
+                uint32_t ent = 0;
+                if constexpr (CODEC == CJ_SNAPPY_RAW) ent = lds32(lut + 4 * (t & 255u));
                 // ---- [C] retire: align, append to the accumulator, store ----
                 {
                     const uint32_t shb = rkind == G4_CK_FAR ? rp_ : (rs & 7u);
@@ -207,9 +219,9 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
                 // ---- [D] decode the next element if the current one is fully issued (plain tags that are in the ring) ----
                 const bool need = active && rem == 0 && !fin;
                 const bool atend = ip >= n;
-                fin = fin || (need && atend);
                 bool slow;
-                {
+                if constexpr (CODEC == CJ_SNAPPY_RAW) {
+                    fin = fin || (need && atend);
                     const bool fast = need && !atend && tw_ok;
                     const uint32_t adv = ent & 0x7Fu, len = (ent >> 8) & 0x7Fu, kind = (ent >> 22) & 3u;
                     const uint32_t off = kind == G4_M1 ? (((ent >> 16) & 7u) << 8) | ((t >> 8) & 0xFFu) : (t >> 8) & 0xFFFFu;
@@ -221,6 +233,33 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
                     sp = take ? (lit ? ip + 1 : off) : sp;
                     rem = take ? len : rem;
                     ip = take ? ip + adv : ip;
+                } else {
+                    // LZ4: a sequence is decoded in two steps, its token (-> the literal run) and, once the literals are issued, its
+                    // offset (-> the match); a token without literals does both at once.  One length-extension byte is taken here,
+                    // longer runs and the end-of-block zone (MFLIMIT / LASTLITERALS rules of lz4_serial_step) go to the slow path.
+                    fin = fin || (need && atend && lz_last);
+                    const bool fast = need && !atend && tw_ok;
+                    const uint32_t b0 = t & 255u, b1 = (t >> 8) & 255u;
+                    const uint32_t ll = b0 >> 4, llx = ll == 15u ? 1u : 0u;
+                    const uint32_t ll_tot = ll + (llx ? b1 : 0u), q = ip + 1 + llx;
+                    const bool lit0 = !lz_phase && ll_tot != 0;
+                    const uint32_t o8 = lz_phase ? 0u : 8u;                       // the offset sits at ip (after literals) or at ip + 1 (no literals)
+                    const uint32_t mln = lz_phase ? lz_ml : (b0 & 15u);
+                    const uint32_t offv = (t >> o8) & 0xFFFFu, xb = (t >> (o8 + 16)) & 255u;
+                    const uint32_t mlx = mln == 15u ? 1u : 0u;
+                    const uint32_t mtot = mln + 4 + (mlx ? xb : 0u), madv = (o8 >> 3) + 2 + mlx;
+                    const bool longrun = lit0 ? (llx && b1 == 255u) : (mlx && xb == 255u);
+                    const bool tailz = !lz_phase && ((uint64_t)opi + ll_tot + 12 > ulen || (uint64_t)q + ll_tot + 8 > n);
+                    const bool mbad = !lit0 && (offv == 0 || offv > opi || (uint64_t)opi + mtot + 5 > ulen);
+                    const bool bad = longrun || tailz || mbad;
+                    const bool take = fast && !bad;
+                    slow = (fast && bad) || (need && !atend && !fast && ip + 4 > n16) || (need && atend && !lz_last);
+                    is_lit = take ? lit0 : is_lit;
+                    sp = take ? (lit0 ? q : offv) : sp;
+                    rem = take ? (lit0 ? ll_tot : mtot) : rem;
+                    ip = take ? (lit0 ? q + ll_tot : ip + madv) : ip;
+                    lz_ml = (take && lit0) ? (b0 & 15u) : lz_ml;
+                    lz_phase = take ? lit0 : lz_phase;
                 }
                 // ---- issue one chunk of the current element ----
                 {
@@ -244,7 +283,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
                 // ---- everything unusual, at most a few times per block ----
                 if (slow) {
                     bool fail = false;
-                    if (rem == 0) {   // tag decode from global memory, with every check
+                    if (rem == 0 && CODEC == CJ_SNAPPY_RAW) {   // tag decode from global memory, with every check
                         uint32_t t = ldg_u8(src + ip);
                         if (ip + 1 < n) t |= ldg_u8(src + ip + 1) << 8;
                         if (ip + 2 < n) t |= ldg_u8(src + ip + 2) << 16;
@@ -267,6 +306,48 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
                             const bool lit = kind == G4_LIT;
                             if (adv > n - ip || len > ulen - opi || (!lit && (off == 0 || off > opi))) fail = true;
                             else { is_lit = lit; sp = lit ? ip + 1 : off; rem = len; ip += adv; }
+                        }
+                    } else if (rem == 0) {   // LZ4, step by step as lz4_serial_step (lz_decode.cuh) does it; whatever it rejects is generation 2's
+                        if (ip >= n) fail = true;
+                        else if (!lz_phase) {
+                            const uint32_t token = ldg_u8(src + ip);
+                            uint32_t p = ip + 1;
+                            uint64_t len = token >> 4;
+                            if (len == 15) {
+                                if (n < 15 || p >= n - 15) fail = true;
+                                else {
+                                    uint32_t bb;
+                                    do {
+                                        bb = ldg_u8(src + p++);
+                                        len += bb;
+                                        if (p > n - 15) { fail = true; break; }
+                                    } while (bb == 255);
+                                }
+                            }
+                            if (!fail) {
+                                if ((uint64_t)opi + len + 12 > ulen || (uint64_t)p + len + 8 > n) {   // must be the final, literal-only sequence
+                                    if ((uint64_t)p + len != n || (uint64_t)opi + len > ulen) fail = true;
+                                    else { is_lit = true; sp = p; rem = (uint32_t)len; ip = n; lz_last = true; }
+                                } else {
+                                    is_lit = true; sp = p; rem = (uint32_t)len; ip = p + (uint32_t)len;
+                                    lz_phase = true; lz_ml = token & 15u;
+                                }
+                            }
+                        } else {
+                            const uint32_t off = ldg_u8(src + ip) | (ldg_u8(src + ip + 1) << 8);
+                            uint32_t p = ip + 2;
+                            uint64_t len = lz_ml;
+                            if (len == 15) {
+                                uint32_t bb;
+                                do {
+                                    bb = ldg_u8(src + p++);
+                                    len += bb;
+                                    if (p > n - 4) { fail = true; break; }
+                                } while (bb == 255);
+                            }
+                            len += 4;
+                            if (fail || off == 0 || off > opi || (uint64_t)opi + len + 5 > ulen) fail = true;
+                            else { is_lit = false; sp = off; rem = (uint32_t)len; ip = p; lz_phase = false; }
                         }
                     } else {          // a literal chunk at the end of the block: staged by hand, retired like a far chunk
                         const uint32_t c = min(rem, 8u);
@@ -313,12 +394,12 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
 #pragma unroll
                 for (int u = 0; u < G4_D; u++) empty = empty && M[u] == 0;
                 if (empty) {
-                    if (opi != ulen) g4_redo(g, cur);
+                    if (CODEC == CJ_SNAPPY_RAW && opi != ulen) g4_redo(g, cur);
                     else {
                         const uint32_t k = opr & 15u;
                         uint8_t* tail = dst + (opr & ~15u);
                         for (uint32_t j = 0; j < k; j++) tail[j] = (uint8_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))));
-                        b.dst_len[cur] = ulen;
+                        b.dst_len[cur] = opi;
                         b.status[cur] = CJ_OK;
                     }
                     active = false;
@@ -332,13 +413,25 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) g4_kernel(Batch b, G4 g) {
 
 cudaError_t launch_lz_decode_list(int codec, const Batch& b, uint32_t* redo_list, unsigned* ctr, int sm_count, cudaStream_t stream);
 
-cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream) {
+template <int CODEC, int D>
+static cudaError_t launch_g4(const Batch& b, const G4& g, int sm_count, cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(g4_kernel<CJ_SNAPPY_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_CTA);
+        cudaError_t e = cudaFuncSetAttribute(g4_kernel<CODEC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4_smem_cta(D, G4_MAX_WARPS));
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    // One CTA per SM, as many warps as the batch needs (a lane per block): the kernel then takes an even share of every
+    // SM, and whatever runs beside it (the warp-per-block kernel of the co-scheduled split) finds room on all of them.
+    const size_t warps = ((size_t)b.n + 31) / 32;
+    const int w = (int)std::min<size_t>(G4_MAX_WARPS, std::max<size_t>(1, (warps + sm_count - 1) / sm_count));
+    const int grid = (int)std::min<size_t>((warps + w - 1) / w, (size_t)sm_count);
+    g4_kernel<CODEC, D><<<grid, w * 32, (size_t)g4_smem_cta(D, w), stream>>>(b, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream) {
+    static const int depth = [] { const char* e = getenv("CJ_G4_D"); return e ? atoi(e) : CJ_G4_D; }();
     const size_t n = b.n;
     if (sc.ensure_fixed((n + 8) * 4 + 64) != 0) return cudaErrorMemoryAllocation;
     G4 g;
@@ -346,10 +439,9 @@ cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_c
     g.redo_list = (uint32_t*)sc.fixed() + 8;
     cudaError_t e = cudaMemsetAsync(g.ctr, 0, 4 * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
-    const int per = G4_WARPS * 32;
-    const int grid = (int)std::min<size_t>((n + per - 1) / per, (size_t)sm_count * 8);
-    g4_kernel<CJ_SNAPPY_RAW><<<grid, per, (size_t)G4_SMEM_CTA, stream>>>(b, g);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (codec == CJ_LZ4_BLOCK) e = depth <= 2 ? launch_g4<CJ_LZ4_BLOCK, 2>(b, g, sm_count, stream) : launch_g4<CJ_LZ4_BLOCK, 3>(b, g, sm_count, stream);
+    else e = depth <= 2 ? launch_g4<CJ_SNAPPY_RAW, 2>(b, g, sm_count, stream) : (depth == 3 ? launch_g4<CJ_SNAPPY_RAW, 3>(b, g, sm_count, stream) : launch_g4<CJ_SNAPPY_RAW, 4>(b, g, sm_count, stream));
+    if (e != cudaSuccess) return e;
     return launch_lz_decode_list(codec, b, g.redo_list, g.ctr, sm_count, stream);
 }
 

@@ -115,8 +115,8 @@ const char* cj_status_string(int32_t status);    /* text used for the Python exc
 uint64_t cj_ctx_launch_count(const cj_ctx* ctx);
 /* Tuning knob, not part of the reference surface: which kernel family decodes LZ4 / Snappy block batches of at least
  * min_units units (smaller batches always take generation 2).  2 = one warp per block; 3 = index walk + lane state
- * machines; 4 = one thread per block (Snappy only); 5 (default, min_units 32768) =
- * generations 4 and 2 side by side on two halves of a Snappy batch.  Results are identical on every path. */
+ * machines; 4 (default, min_units 32768) = one thread per block (Snappy only);
+ * 5 = generations 4 and 2 side by side on two parts of a Snappy batch.  Results are identical on every path. */
 int cj_ctx_set_decode_path(cj_ctx* ctx, int generation, long min_units);
 int cj_ctx_get_decode_path(const cj_ctx* ctx, int* generation, long* min_units);
 /* Device-side duration in milliseconds of the codec kernels of the most recent batch call
