@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                     const uint32_t fs = opi - sp;
                     const uint8_t* gp = dst + (fs & ~7u);
                     g4_cp_async8_if(stl + u * 512, gp, isfar ? 1u : 0u);
-                    g4_cp_async8_if(stl + u * 512 + 8, gp + 8, isfar ? 1u : 0u);
+                    g4_cp_async8_if(stl + u * 512 + 8, gp + 8, (isfar && (fs & 7u) + c > 8) ? 1u : 0u);   // second half only if the chunk reaches into it
                     const uint32_t kind = is_lit ? G4_CK_LIT : (isnear ? G4_CK_NEAR : G4_CK_FAR);
                     M[u] = c ? (c | (kind << 4)) : 0u;
                     P[u] = (is_lit || isnear) ? sp : (fs & 7u);
