@@ -59,6 +59,7 @@ def lib():
         "cj_ctx_launch_count": ([vp], u64),
         "cj_ctx_set_decode_path": ([vp, C.c_int, C.c_long], C.c_int),
         "cj_ctx_get_decode_path": ([vp, C.POINTER(C.c_int), C.POINTER(C.c_long)], C.c_int),
+        "cj_ctx_last_redo_count": ([vp, C.POINTER(C.c_uint)], C.c_int),
         "cj_ctx_last_kernel_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "cj_compress_bound": ([C.c_int, sz], sz),
         "cj_decompressed_len": ([C.c_int, vp, sz, C.POINTER(sz)], C.c_int),
@@ -146,6 +147,12 @@ class Context:
         """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 3 = index walk + lane
         state machines, 4 = one thread per block (Snappy; the default), 5 = 4 and 2 side by side on a split Snappy batch."""
         _check(lib().cj_ctx_set_decode_path(self._h, generation, min_units))
+
+    def last_redo_count(self):
+        """Units of the most recent generation-4 batch that were handed to the generation-2 kernel."""
+        v = C.c_uint()
+        _check(lib().cj_ctx_last_redo_count(self._h, C.byref(v)))
+        return v.value
 
     def decode_path(self):
         g, m = C.c_int(), C.c_long()

@@ -132,6 +132,19 @@ int cj_ctx_get_decode_path(const cj_ctx* c, int* generation, long* min_units) {
     return CJ_OK;
 }
 
+int cj_ctx_last_redo_count(cj_ctx* c, unsigned* out) {
+    if (!c || !out) return CJ_E_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    *out = 0;
+    if (!c->g3.fixed() || !c->redo_valid) return CJ_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    unsigned ctr[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(ctr, c->redo_ctr, sizeof ctr, cudaMemcpyDeviceToHost));
+    *out = ctr[1];
+    return CJ_OK;
+}
+
 int cj_ctx_last_kernel_ms(cj_ctx* c, float* ms) {
     if (!c || !ms) return CJ_E_INVALID_ARG;
     if (!c->ev_valid) {
@@ -193,8 +206,11 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
                 c->launches += 2;   // thread-per-block kernel + its redo list + the warp-per-block kernel
             } else if (c->decode_gen == 4 && reset_counter && (long)b.n >= c->g3_min_units) {
                 e = cj::launch_lz_decode4(codec, b, c->g3, c->sm_count, c->stream);
+                c->redo_ctr = (const unsigned*)c->g3.fixed();   // lz_decode4.cu keeps its counters at the start of the scratch
+                c->redo_valid = true;
                 c->launches += 1;
             } else if (c->decode_gen == 3 && reset_counter && (long)b.n >= c->g3_min_units) {
+                c->redo_valid = false;   // the scratch is re-laid out by this path
                 e = cj::launch_lz_decode3(codec, b, c->g3, c->sm_count, c->stream);
                 c->launches += 3;
             } else {

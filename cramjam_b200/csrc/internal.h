@@ -112,6 +112,8 @@ struct cj_ctx {
                                    // (lz_decode4.cu, Snappy), the default for large batches), 5 = 4 and 2 side by side on a split batch (Snappy)
     long g3_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
     int g4_share = 50;             // decode_gen 5: percentage of a Snappy batch given to the thread-per-block kernel, the rest runs concurrently on generation 2
+    const unsigned* redo_ctr = nullptr;   // device counters of the most recent generation-4 launch ([1] = units handed to generation 2)
+    bool redo_valid = false;
     cudaStream_t s_aux = nullptr;  // second stream of that split
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;

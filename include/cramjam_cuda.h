@@ -119,6 +119,8 @@ uint64_t cj_ctx_launch_count(const cj_ctx* ctx);
  * 5 = generations 4 and 2 side by side on two parts of a Snappy batch.  Results are identical on every path. */
 int cj_ctx_set_decode_path(cj_ctx* ctx, int generation, long min_units);
 int cj_ctx_get_decode_path(const cj_ctx* ctx, int* generation, long* min_units);
+/* Diagnostics: how many units of the most recent generation-4 batch were handed to the generation-2 kernel (waits for the stream). */
+int cj_ctx_last_redo_count(cj_ctx* ctx, unsigned* out);
 /* Device-side duration in milliseconds of the codec kernels of the most recent batch call
  * (CUDA events on the context's stream; waits for them). */
 int cj_ctx_last_kernel_ms(cj_ctx* ctx, float* ms);

@@ -42,6 +42,8 @@ def test_synthetic_blocks_bit_exact(codec):
     dst, do, dl, st = gpu_decode_device(codec, src, so, sl, [U] * n)
     assert (st == 0).all() and (dl == U).all()
     assert np.array_equal(dst[:n * U], data)
+    if ctx().decode_path()[0] == 4:   # well-formed, aligned blocks are decoded by the thread-per-block kernel itself, not by its fallback
+        assert ctx().last_redo_count() == 0
 
 
 @pytest.mark.parametrize("codec", [capi.SNAPPY_RAW, capi.LZ4_BLOCK])
