@@ -26,9 +26,9 @@ namespace cj {
 #ifndef CJ_G4_D
 #define CJ_G4_D 3
 #endif
-constexpr int G4_MAX_WARPS = 16;       // warps per CTA: chosen at launch so that one CTA per SM holds the whole batch when it fits
+constexpr int G4_MAX_WARPS = 20;       // warps per CTA (96 registers x 640 threads fill the register file): chosen at launch, see launch_g4
 constexpr int G4_DMAX = 4;             // sub-iterations between issue and retire of a chunk: template parameter D <= G4_DMAX
-constexpr uint32_t G4_INB = 256;       // input ring bytes per lane
+constexpr uint32_t G4_INB = 128;       // input ring bytes per lane (8 granules of 16 bytes)
 constexpr uint32_t G4_RECB = 128;      // recent-output mirror bytes per lane
 constexpr uint32_t G4_NEAR = 64;       // back-references up to this offset are read from the mirror at retire time
 constexpr int g4_smem_warp(int D) { return 32 * (int)(G4_INB + G4_RECB + 16 * D); }   // + one 16-byte staging slot per chunk in flight
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
         for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(lut + 4 * t, g4_tag_entry(t));
         __syncthreads();
     }
-    auto in_a = [&](uint32_t x) -> uint32_t { return inl + ((x & 0xF0u) << 5) + (x & 15u); };
+    auto in_a = [&](uint32_t x) -> uint32_t { return inl + ((x & (G4_INB - 16)) << 5) + (x & 15u); };
     auto rec_s = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5); };             // mirror slot (16 bytes) holding output byte p
     auto rec_a = [&](uint32_t p) -> uint32_t { return recl + ((p & 0x70u) << 5) + (p & 8u); };   // its 8-byte half
     const uint32_t nwarps = gridDim.x * G4_WARPS;
@@ -167,17 +167,18 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
         uint32_t tw0 = 0, tw1 = 0;       // the two ring words around ip, fetched one sub-iteration ahead
         bool tw_ok = false;              // ... and whether they had arrived in the ring when they were fetched
         uint32_t M[G4_D], P[G4_D];       // chunk in flight: M = bytes | kind << 4;  P = input position / offset / byte shift
+        uint32_t L[G4_D];                // `loaded` as it was at the end of the slot's previous visit
 #pragma unroll
-        for (int u = 0; u < G4_D; u++) { M[u] = 0; P[u] = 0; }
+        for (int u = 0; u < G4_D; u++) { M[u] = 0; P[u] = 0; L[u] = 0; }
 
         // The loop body is written without branches on the common path (selects and predicated PTX), so that the retire
         // chain, the tag-decode chain and the issue of the next chunk interleave inside one basic block: with one thread
         // per block only ~3.5 warps share a scheduler, and instruction-level parallelism has to hide what they cannot.
         while (__any_sync(FULL, active)) {
-            lim = loaded;   // granules requested one whole iteration ago have arrived (wait_group below)
 #pragma unroll
             for (int u = 0; u < G4_D; u++) {
                 asm volatile("cp.async.wait_group %0;" ::"n"(G4_D - 1) : "memory");
+                lim = L[u];   // what had been requested when this slot was last visited has arrived now
                 // Shared-memory accesses are volatile asm and keep their program order, so the loads of the two independent
                 // chains (retire, tag decode) are written first and their arithmetic afterwards.
                 // ---- [A] retire: load the source window of the chunk issued G4_D sub-iterations ago (in shared memory by now) ----
@@ -187,6 +188,8 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                 const uint32_t rsa = stl + u * 512;
                 const uint32_t ra = rkind == G4_CK_LIT ? in_a(rs0) : (rkind == G4_CK_NEAR ? rec_a(rs0) : rsa);
                 const uint32_t ra2 = rkind == G4_CK_LIT ? in_a(rs1) : (rkind == G4_CK_NEAR ? rec_a(rs1) : rsa + 8);
+                // the mirror always holds the completed 16-byte words; a near chunk also needs the bytes still in the accumulator
+                g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), rkind == G4_CK_NEAR ? 1u : 0u);
                 const uint2 a0 = g4_lds64(ra), a1 = g4_lds64(ra2);
                 // ---- [B] tag decode: table entry of the tag fetched at the end of the previous sub-iteration ----
                 const uint32_t t = __funnelshift_r(tw0, tw1, (ip & 3u) * 8);
@@ -209,12 +212,11 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                     lo |= lowhalf ? vl : 0ull;
                     hi |= lowhalf ? vh : vl;
                     const uint32_t cross = k + rc >= 16 ? 1u : 0u;   // the 16-byte word is complete (only from the upper half)
-                    g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), 1u);
+                    g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), cross);
                     g4_stg128_if(dst + (opr & ~15u), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), cross);
                     lo = cross ? vh : lo;
                     hi = cross ? 0ull : hi;
                     opr += rc;
-                    g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), 0u, 0u, cross);   // the spilled bytes open the next mirror slot
                 }
                 // ---- [D] decode the next element if the current one is fully issued (plain tags that are in the ring) ----
                 const bool need = active && rem == 0 && !fin;
@@ -375,16 +377,14 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                 tw0 = lds32(in_a(ip & ~3u));
                 tw1 = lds32(in_a((ip & ~3u) + 4));
                 tw_ok = ip + 4 <= lim;
-                // ---- input ring, once per iteration: up to two more granules if they fit ahead of everything still needed ----
-                if (u == 0) {
+                // ---- input ring: one more granule if it fits ahead of everything still needed ----
+                {
                     const uint32_t rp = (rem && is_lit) ? sp : ip;
                     const uint32_t keep = (rp > 16u * G4_D ? rp - 16u * G4_D : 0u) & ~15u;   // chunks in flight read at most this far back
-#pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const bool go = active && loaded < n16 && loaded <= keep + (G4_INB - 16);
-                        g4_cp_async16_if(inl + ((loaded & 0xF0u) << 5), src + loaded, go ? 1u : 0u);
-                        loaded += go ? 16u : 0u;
-                    }
+                    const bool go = active && loaded < n16 && loaded <= keep + (G4_INB - 16);
+                    g4_cp_async16_if(inl + ((loaded & (G4_INB - 16)) << 5), src + loaded, go ? 1u : 0u);
+                    loaded += go ? 16u : 0u;
+                    L[u] = loaded;
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
@@ -424,9 +424,24 @@ static cudaError_t launch_g4(const Batch& b, const G4& g, int sm_count, cudaStre
     // One CTA per SM, as many warps as the batch needs (a lane per block): the kernel then takes an even share of every
     // SM, and whatever runs beside it (the warp-per-block kernel of the co-scheduled split) finds room on all of them.
     const size_t warps = ((size_t)b.n + 31) / 32;
-    const int w = (int)std::min<size_t>(G4_MAX_WARPS, std::max<size_t>(1, (warps + sm_count - 1) / sm_count));
-    const int grid = (int)std::min<size_t>((warps + w - 1) / w, (size_t)sm_count);
-    g4_kernel<CODEC, D><<<grid, w * 32, (size_t)g4_smem_cta(D, w), stream>>>(b, g);
+    static const int force_w = [] { const char* e = getenv("CJ_G4_WARPS"); return e ? atoi(e) : 0; }();       // experiments: warps per CTA
+    // batches beyond sm_count x G4_MAX_WARPS x 32 blocks are decoded in several equal rounds by the same CTAs
+    const size_t rounds = std::max<size_t>(1, (warps + (size_t)sm_count * G4_MAX_WARPS - 1) / ((size_t)sm_count * G4_MAX_WARPS));
+    int w = (int)std::min<size_t>(G4_MAX_WARPS, std::max<size_t>(1, (warps + (size_t)sm_count * rounds - 1) / ((size_t)sm_count * rounds)));
+    if (force_w >= 1 && force_w <= G4_MAX_WARPS) w = force_w;
+    const int grid = (int)std::min<size_t>((warps + w - 1) / w, (size_t)sm_count * (size_t)std::max(1, G4_MAX_WARPS / w));
+    const size_t smem = (size_t)g4_smem_cta(D, w);
+    // The L1 share of the 256 KB SM memory decides this kernel's speed (re-reads of back-reference sectors hit it): ask for the
+    // smallest shared-memory carve-out that holds the CTAs of one SM (8.8 ms with 60 KB of L1, 14.4 ms with 28 KB).
+    static int carve_for_w = -1;
+    if (carve_for_w != w) {
+        const int per_sm = (grid + sm_count - 1) / sm_count;
+        const int pct = (int)std::min<size_t>(100, ((smem + 1024) * per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(g4_kernel<CODEC, D>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e != cudaSuccess) return e;
+        carve_for_w = w;
+    }
+    g4_kernel<CODEC, D><<<grid, w * 32, smem, stream>>>(b, g);
     return cudaGetLastError();
 }
 
