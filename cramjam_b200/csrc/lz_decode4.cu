@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                 const uint32_t rs = rkind == G4_CK_LIT ? rp_ : opr - rp_;
                 const uint32_t rs0 = rs & ~7u, rs1 = rs0 + 8;
                 const uint32_t rsa = stl + u * 512;
-                const uint32_t ra = rkind == G4_CK_LIT ? in_a(rs0) : (rkind == G4_CK_NEAR ? rec_a(rs0) : rsa);
-                const uint32_t ra2 = rkind == G4_CK_LIT ? in_a(rs1) : (rkind == G4_CK_NEAR ? rec_a(rs1) : rsa + 8);
+                // input ring and mirror have the same geometry (8 granules of 16 bytes, 512 bytes apart): one address form, two bases
+                static_assert(G4_INB == G4_RECB, "retire addresses assume equal ring geometry");
+                const uint32_t rbase = rkind == G4_CK_LIT ? inl : recl;
+                const uint32_t ra = rkind == G4_CK_FAR ? rsa : rbase + ((rs0 & 0x70u) << 5) + (rs0 & 8u);
+                const uint32_t ra2 = rkind == G4_CK_FAR ? rsa + 8 : rbase + ((rs1 & 0x70u) << 5) + (rs1 & 8u);
                 // the mirror always holds the completed 16-byte words; a near chunk also needs the bytes still in the accumulator
                 g4_sts128(rec_s(opr), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32), rkind == G4_CK_NEAR ? 1u : 0u);
                 const uint2 a0 = g4_lds64(ra), a1 = g4_lds64(ra2);
@@ -205,7 +208,11 @@ __global__ void __launch_bounds__(G4_MAX_WARPS * 32, 1) g4_kernel(Batch b, G4 g)
                         if (rp_ < 4) v |= v << (16 * rp_);
                         if (rp_ < 2) v |= v << 32;
                     }
-                    v = rc ? v & (~0ull >> (64 - 8 * rc)) : 0ull;
+                    {   // keep the chunk's rc bytes: two clamped funnel shifts build the 32-bit halves of the mask (rc = 0 gives 0)
+                        const uint32_t mlo = __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * min(rc, 4u));
+                        const uint32_t mhi = __funnelshift_rc(0xFFFFFFFFu, 0u, 64u - 8u * max(rc, 4u));
+                        v &= ((uint64_t)mhi << 32) | mlo;
+                    }
                     const uint32_t k = opr & 15u, sh = (k & 7u) * 8;
                     const uint64_t vl = v << sh, vh = sh ? v >> (64 - sh) : 0ull;
                     const bool lowhalf = k < 8;
