@@ -1,21 +1,26 @@
-// lz_decode4.cu — generation-4 batch decode of Snappy raw blocks (sm_100a): one THREAD per block.
+// lz_decode4.cu — generation-4 batch decode of Snappy raw blocks and LZ4 blocks (sm_100a): one THREAD per block.
 //
-// Same reference entry point as lz_decode.cuh (snap::raw::Decoder::decompress behind cramjam.snappy.decompress_raw /
-// decompress_raw_into, src/snappy.rs:52-60,102-108).  Generations 2 and 3 spend 20-30 warp instructions per ~8-byte
-// element because a whole warp cooperates on one block; here a lane owns a block and decodes it the way a CPU does,
-// so one warp instruction advances 32 blocks.  What makes that workable on a GPU:
+// Same reference entry points as lz_decode.cuh (snap::raw::Decoder::decompress behind cramjam.snappy.decompress_raw /
+// decompress_raw_into, src/snappy.rs:52-60,102-108; LZ4_decompress_safe behind lz4::block::decompress_into,
+// src/lz4.rs:78-95,140-173).  Generations 2 and 3 spend 20-30 warp instructions per ~8-byte element because a whole warp
+// cooperates on one block; here a lane owns a block and decodes it the way a CPU does, so one warp instruction advances
+// 32 blocks.  What makes that workable on a GPU:
 //
-//   * compressed input reaches a lane through its own 256-byte shared-memory ring, filled 16 bytes at a time by the
-//     lane's own cp.async (no cooperation, no shuffles), running up to 240 bytes ahead of the read cursor;
-//   * every sub-iteration moves at most one 8-byte CHUNK of the lane's current element.  A chunk is ISSUED (its source
-//     words are loaded: literal bytes from the input ring, back-reference bytes from the block's own output in global
-//     memory) and RETIRED G4_D sub-iterations later (shift to the output alignment, append to a 16-byte register
-//     accumulator, one aligned 16-byte st.global per 16 bytes of output), so the L2/DRAM latency of a back-reference
-//     is overlapped with the following elements instead of being waited for;
-//   * back-references that reach into bytes not yet stored (offset <= 64) are read at retire time from a 128-byte
+//   * compressed input reaches a lane through its own 128-byte shared-memory ring, filled 16 bytes per sub-iteration by
+//     the lane's own cp.async (no cooperation, no shuffles), 64-80 bytes ahead of the read cursor;
+//   * every sub-iteration a lane ISSUES at most one 8-byte CHUNK of its current element and RETIRES the chunk it issued
+//     D sub-iterations earlier.  Issue starts the source fetch: literal bytes are in the input ring already, a
+//     back-reference further than 64 bytes is fetched from the block's own output in global memory by cp.async into a
+//     per-lane staging slot (asynchronous: no register scoreboard is held across the loop back-edge).  Retire reads 16
+//     bytes from shared memory, shifts them to the output alignment, appends them to a 16-byte register accumulator and
+//     stores a completed word with one aligned 16-byte st.global;
+//   * back-references that may reach into bytes not yet stored (offset <= 64) are read at retire time from a 128-byte
 //     per-lane mirror of the most recent output in shared memory; offsets below 8 are expanded to a periodic pattern;
-//   * both rings are interleaved across lanes in 16-byte granules, so lane-private accesses at unrelated positions
-//     fall into different banks.
+//   * rings, mirror and staging slots are interleaved across lanes in 16-byte granules, so lane-private accesses at
+//     unrelated positions fall into different banks;
+//   * the common path has no branches (selects, predicated PTX); everything unusual takes one slow branch;
+//   * one CTA per SM with as many warps as the batch needs and the smallest shared-memory carve-out that holds it: the
+//     L1 share of the SM decides the kernel's speed (re-reads of back-reference sectors hit it).
 //   Anything unusual (unaligned unit, 4-byte-offset copy, malformed element, bad offset, length mismatch) puts the
 //   block on the redo list of the generation-2 kernel, which owns all error reporting: status codes stay the oracle's.
 #include "internal.h"
@@ -46,12 +51,6 @@ __device__ __forceinline__ void g4_redo(const G4& g, uint32_t u) {
     g.redo_list[i] = u;
 }
 
-__device__ __forceinline__ void g4_cp_async16(uint32_t saddr, const void* gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void g4_cp_async8(uint32_t saddr, const void* gptr) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
-}
 // predicated forms (no branch around them)
 __device__ __forceinline__ void g4_cp_async8_if(uint32_t saddr, const void* gptr, uint32_t pred) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(saddr), "l"(gptr), "r"(pred) : "memory");
@@ -69,14 +68,6 @@ __device__ __forceinline__ uint2 g4_lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
-}
-__device__ __forceinline__ uint2 g4_ldg64(const void* p) {   // coherent load: re-reads output this thread stored earlier
-    uint2 v;
-    asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void g4_stg128(void* p, uint4 v) {
-    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // 8 bytes starting `shb` (0..7) bytes into the 16-byte window {a0, a1}
