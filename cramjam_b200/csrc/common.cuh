@@ -5,6 +5,17 @@
 
 #include "../../include/cramjam_cuda.h"
 
+// Kernel function attributes (dynamic shared-memory limit, carve-out) belong to the device the call is made on: launchers keep
+// one flag per device, not one per process, so that a second context on another GPU sets them again.
+struct cj_per_device_flag {
+    int v[64] = {};
+    int& here() {
+        int d = 0;
+        (void)cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 namespace cj {
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -323,11 +323,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz4f_decode_kerne
 
 cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)DEC_SMEM_WARP * DEC_WARPS;
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(lz4f_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     int grid = sm_count * CJ_DEC_CTAS;
     const int need = (int)((b.n + DEC_WARPS - 1) / DEC_WARPS);

@@ -36,11 +36,12 @@ template <int CODEC, bool FAST>
 static cudaError_t launch_one(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
     const size_t smem = (size_t)DEC_SMEM_WARP * DEC_WARPS;
     auto k = lz_decode_kernel<CODEC, FAST>;
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     int grid = sm_count * CJ_DEC_CTAS;  // CTAs per SM x 4 warps x (ORING + IRING + 256 B) of shared memory
     const int need = (int)((b.n + DEC_WARPS - 1) / DEC_WARPS);

@@ -672,13 +672,14 @@ static cudaError_t set_smem(K k, size_t bytes) {
 
 template <int CODEC>
 static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream, G3Debug* dbg) {
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e;
         if ((e = set_smem(g3_index_kernel<CODEC>, (size_t)IX_SMEM_CTA)) != cudaSuccess) return e;
         if ((e = set_smem(g3_exec_kernel<CODEC>, (size_t)X_SMEM_WARP * X_WARPS)) != cudaSuccess) return e;
         if ((e = set_smem(lz_decode_list_kernel<CODEC>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     const size_t n = b.n;
     // fixed part: desc_off[n+1] count[n] ulen[n] redo_list[n] ctr[4] total
@@ -733,12 +734,13 @@ static cudaError_t launch_g3(const Batch& b, G3Scratch& sc, int sm_count, cudaSt
 
 // The generation-2 kernel over a redo list filled by another path (lz_decode4.cu): ctr[1] = entries, ctr[2] = work queue.
 cudaError_t launch_lz_decode_list(int codec, const Batch& b, uint32_t* redo_list, unsigned* ctr, int sm_count, cudaStream_t stream) {
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e;
         if ((e = set_smem(lz_decode_list_kernel<CJ_SNAPPY_RAW>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
         if ((e = set_smem(lz_decode_list_kernel<CJ_LZ4_BLOCK>, (size_t)DEC_SMEM_WARP * DEC_WARPS)) != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     G3 g{};
     g.redo_list = redo_list;

@@ -413,11 +413,12 @@ cudaError_t launch_lz_decode_list(int codec, const Batch& b, uint32_t* redo_list
 
 template <int CODEC, int D>
 static cudaError_t launch_g4(const Batch& b, const G4& g, int sm_count, cudaStream_t stream) {
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(g4_kernel<CODEC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, g4_smem_cta(D, G4_MAX_WARPS));
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     // One CTA per SM, as many warps as the batch needs (a lane per block): the kernel then takes an even share of every
     // SM, and whatever runs beside it (the warp-per-block kernel of the co-scheduled split) finds room on all of them.
@@ -431,7 +432,8 @@ static cudaError_t launch_g4(const Batch& b, const G4& g, int sm_count, cudaStre
     const size_t smem = (size_t)g4_smem_cta(D, w);
     // The L1 share of the 256 KB SM memory decides this kernel's speed (re-reads of back-reference sectors hit it): ask for the
     // smallest shared-memory carve-out that holds the CTAs of one SM (8.8 ms with 60 KB of L1, 14.4 ms with 28 KB).
-    static int carve_for_w = -1;
+    static cj_per_device_flag carve_flag;   // warps per CTA the carve-out was last set for on this device
+    int& carve_for_w = carve_flag.here();
     if (carve_for_w != w) {
         const int per_sm = (grid + sm_count - 1) / sm_count;
         const int pct = (int)std::min<size_t>(100, ((smem + 1024) * per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));

@@ -244,7 +244,8 @@ template <int CODEC, int HBITS>
 static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
     const size_t smem = (sizeof(enc_slot_t) << HBITS) * ENC_WARPS;
     auto k = lz_encode_kernel<CODEC, HBITS>;
-    static int ctas_per_sm = 0;
+    static cj_per_device_flag ctas_flag;
+    int& ctas_per_sm = ctas_flag.here();
     if (!ctas_per_sm) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

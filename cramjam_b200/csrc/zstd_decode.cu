@@ -678,11 +678,12 @@ size_t zstd_scratch_bytes(int sm_count, uint32_t n) { return (size_t)zstd_grid(s
 
 cudaError_t launch_zstd_decode(const Batch& b, unsigned* counter, uint8_t* lit_scratch, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)ZS_SMEM_WARP * ZS_WARPS;
-    static bool attr_done = false;
+    static cj_per_device_flag attr_flag;
+    int& attr_done = attr_flag.here();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = 1;
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
