@@ -37,6 +37,26 @@ def test_compress_bounds():
     assert L.cj_compress_bound(capi.LZ4_BLOCK, 0x7E000001) == 0
 
 
+def _frame_piece(n):
+    """Chunk / block size the frame encoders cut an input of n bytes into (frames.cu frame_piece)."""
+    if n >= 4 << 20:
+        return 65536
+    return min(65536, max(16384, (n // 64 + 4095) & ~4095))
+
+
+def test_frame_bounds_cover_the_finer_chunks_of_small_inputs():
+    """Inputs under 4 MiB are cut into 16-64 KiB chunks (more warps per call): the bounds must hold an incompressible input,
+    every chunk stored raw with its own header (the case a 65 535-byte random input once missed by 3 bytes)."""
+    capi = _lib()
+    L = capi.lib()
+    for n in (0, 1, 15, 16383, 16384, 16385, 65535, 65536, 65537, 200000, (1 << 20) - 1, 1 << 20, (4 << 20) - 1, 4 << 20, (4 << 20) + 1, 100 << 20):
+        piece = _frame_piece(n)
+        chunks = (n + piece - 1) // piece
+        assert chunks <= max(64, n // 65536 + 1)
+        assert L.cj_compress_bound(capi.SNAPPY_FRAMED, n) >= 10 + chunks * 8 + n          # stream id + (type, len, crc) per chunk
+        assert L.cj_compress_bound(capi.LZ4_FRAME, n) >= 15 + chunks * 4 + n + 8          # header + block sizes + end mark + content checksum
+
+
 def test_synth_host_is_deterministic_and_shaped():
     capi = _lib()
     a = capi.synth_host(8, 65536, seed=1, first_index=5)
