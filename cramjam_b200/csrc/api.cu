@@ -69,8 +69,14 @@ int cj_ctx_create(int device, cj_ctx** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("CJ_DECODE_GEN")) c->decode_gen = atoi(v);
-    if (const char* v = getenv("CJ_G3_MIN_UNITS")) c->g3_min_units = atol(v);
-    if (const char* v = getenv("CJ_G4_SHARE")) c->g4_share = std::min(100, std::max(0, atoi(v)));
+    if (c->decode_gen != 2 && c->decode_gen != 4) c->decode_gen = 4;
+    if (const char* v = getenv("CJ_G4_MIN_UNITS")) c->g4_min_units = atol(v);
+    // The thread-per-block decoder's far back-reference fetches are 16-byte reads scattered over 4 GiB of live windows:
+    // with the default 64-byte L2 fetch granularity every miss drags a second, unused sector in from DRAM.
+    if (const char* v = getenv("CJ_L2_FETCH")) {
+        const int g = atoi(v);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUDA_TRY(cudaMalloc(&c->counters, 64 * sizeof(unsigned)));
@@ -88,9 +94,6 @@ void cj_ctx_destroy(cj_ctx* c) {
     if (c->counters) cudaFree(c->counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->s_aux) cudaStreamDestroy(c->s_aux);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int i = 0; i < cj_ctx::PIPE; i++) {
@@ -118,17 +121,17 @@ int cj_ctx_synchronize(cj_ctx* c) {
 uint64_t cj_ctx_launch_count(const cj_ctx* c) { return c ? c->launches : 0; }
 
 int cj_ctx_set_decode_path(cj_ctx* c, int generation, long min_units) {
-    if (!c || (generation < 2 || generation > 5) || min_units < 1) return CJ_E_INVALID_ARG;
+    if (!c || (generation != 2 && generation != 4) || min_units < 1) return CJ_E_INVALID_ARG;
     std::lock_guard<std::mutex> g(c->mu);
     c->decode_gen = generation;
-    c->g3_min_units = min_units;
+    c->g4_min_units = min_units;
     return CJ_OK;
 }
 
 int cj_ctx_get_decode_path(const cj_ctx* c, int* generation, long* min_units) {
     if (!c) return CJ_E_INVALID_ARG;
     if (generation) *generation = c->decode_gen;
-    if (min_units) *min_units = c->g3_min_units;
+    if (min_units) *min_units = c->g4_min_units;
     return CJ_OK;
 }
 
@@ -136,7 +139,7 @@ int cj_ctx_last_redo_count(cj_ctx* c, unsigned* out) {
     if (!c || !out) return CJ_E_INVALID_ARG;
     std::lock_guard<std::mutex> g(c->mu);
     *out = 0;
-    if (!c->g3.fixed() || !c->redo_valid) return CJ_OK;
+    if (!c->g4.fixed() || !c->redo_valid) return CJ_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     unsigned ctr[4] = {0, 0, 0, 0};
@@ -182,37 +185,13 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
-            // Large Snappy batches take the thread-per-block kernel (4); generation 3 and the co-scheduled split (5) are opt-in
-            // through cj_ctx_set_decode_path() / CJ_DECODE_GEN, everything else is generation 2.
-            if (c->decode_gen == 5 && codec == CJ_SNAPPY_RAW && reset_counter && (long)b.n >= c->g3_min_units && b.n >= 256) {
-                // Co-scheduled split: the thread-per-block kernel (bound by DRAM transactions and latency, ~1/3 of the issue slots)
-                // and the warp-per-block kernel (bound by issue slots, little DRAM traffic) run side by side on the same SMs.
-                if (!c->s_aux) {
-                    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-                    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-                    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-                }
-                const uint32_t n4 = (uint32_t)((uint64_t)b.n * (uint64_t)c->g4_share / 100) & ~63u;
-                cj::Batch b4 = b, b2 = b;
-                b4.n = n4;
-                b2.n = b.n - n4;
-                b2.src_off += n4; b2.src_len += n4; b2.dst_off += n4; b2.dst_cap += n4; b2.dst_len += n4; b2.status += n4;
-                CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
-                CUDA_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-                e = n4 ? cj::launch_lz_decode4(codec, b4, c->g3, c->sm_count, c->stream) : cudaSuccess;
-                if (e == cudaSuccess && b2.n) e = cj::launch_lz_decode(codec, b2, c->counters + 63, c->sm_count, c->s_aux, true);
-                CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
-                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-                c->launches += 2;   // thread-per-block kernel + its redo list + the warp-per-block kernel
-            } else if (c->decode_gen == 4 && reset_counter && (long)b.n >= c->g3_min_units) {
-                e = cj::launch_lz_decode4(codec, b, c->g3, c->sm_count, c->stream);
-                c->redo_ctr = (const unsigned*)c->g3.fixed();   // lz_decode4.cu keeps its counters at the start of the scratch
+            // Large batches take the thread-per-block kernel (generation 4); everything else, and whatever it
+            // declines, the warp-per-block kernel (generation 2).  cj_ctx_set_decode_path() / CJ_DECODE_GEN select.
+            if (c->decode_gen == 4 && reset_counter && (long)b.n >= c->g4_min_units) {
+                e = cj::launch_lz_decode4(codec, b, c->g4, c->sm_count, c->stream);
+                c->redo_ctr = (const unsigned*)c->g4.fixed();   // lz_decode4.cu keeps its counters at the start of the scratch
                 c->redo_valid = true;
                 c->launches += 1;
-            } else if (c->decode_gen == 3 && reset_counter && (long)b.n >= c->g3_min_units) {
-                c->redo_valid = false;   // the scratch is re-laid out by this path
-                e = cj::launch_lz_decode3(codec, b, c->g3, c->sm_count, c->stream);
-                c->launches += 3;
             } else {
                 e = cj::launch_lz_decode(codec, b, counters, c->sm_count, c->stream, reset_counter);
             }
@@ -249,6 +228,33 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         return CJ_E_CUDA;
     }
     return CJ_OK;
+}
+
+// Sends the produced bytes of units [a, b) from the device arena (same offsets, rebased by d_lo) to the caller's pinned
+// memory.  Units that filled their slot and whose slots touch exactly are merged into one copy, so a dense batch of
+// exact-size slots is a single DMA; a gap between slots (padding, an interleaved header) or a short unit ends the run,
+// so no byte of the caller's memory outside [dst_off[i], dst_off[i] + dst_len[i]) is ever written.
+static int copy_runs_home(cj_ctx* c, const cj_batch* bt, const uint64_t* dl, size_t a, size_t b, uint64_t d_lo, uint8_t* hd, cudaStream_t s) {
+    uint64_t run_lo = 0, run_hi = 0;
+    bool open = false;
+    auto flush = [&]() -> int {
+        if (open && run_hi > run_lo)
+            CUDA_TRY(cudaMemcpyAsync(hd + run_lo, (uint8_t*)c->d_dst.p + (run_lo - d_lo), (size_t)(run_hi - run_lo), cudaMemcpyDeviceToHost, s));
+        open = false;
+        return CJ_OK;
+    };
+    int rc;
+    for (size_t i = a; i < b; i++) {
+        if (!dl[i]) continue;
+        if (!open || bt->dst_off[i] != run_hi) {
+            if ((rc = flush())) return rc;
+            run_lo = bt->dst_off[i];
+            open = true;
+        }
+        run_hi = bt->dst_off[i] + dl[i];
+        if (dl[i] != bt->dst_cap[i] && (rc = flush())) return rc;   // a short unit: the next slot does not start where this one's bytes end
+    }
+    return flush();
 }
 
 // Dense pinned arenas, units in ascending order on both sides: split the batch into chunks and run
@@ -331,15 +337,7 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
         if (a == b) continue;
         CUDA_TRY(cudaEventSynchronize(c->ev_k[k]));
         if (trace) fprintf(stderr, "[cj] chunk %d kernel done at %.2f ms\n", k, ms_now());
-        bool tight = true;
-        for (size_t i = a; i < b && tight; i++) tight = dl[i] == bt->dst_cap[i];
-        if (tight) {
-            const uint64_t lo = bt->dst_off[a] - d_lo, hi = bt->dst_off[b - 1] + bt->dst_cap[b - 1] - d_lo;
-            CUDA_TRY(cudaMemcpyAsync(hd + d_lo + lo, (uint8_t*)c->d_dst.p + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->s_d2h));
-        } else {
-            for (size_t i = a; i < b; i++)
-                if (dl[i]) CUDA_TRY(cudaMemcpyAsync(hd + bt->dst_off[i], (uint8_t*)c->d_dst.p + (bt->dst_off[i] - d_lo), (size_t)dl[i], cudaMemcpyDeviceToHost, c->s_d2h));
-        }
+        if ((rc = copy_runs_home(c, bt, dl, a, b, d_lo, hd, c->s_d2h))) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -449,9 +447,11 @@ static int run_host(cj_ctx* c, int codec, bool compress, int where, const cj_bat
         // filled its capacity; otherwise fall through to the per-unit path so that no byte past
         // dst_len[i] of the caller's memory is touched.
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        // (ascending, exactly touching slots only: a gap between slots belongs to the caller and stays untouched)
         tight = true;
         const uint64_t* dl = hq + 4 * n;
-        for (size_t i = 0; i < n && tight; i++) tight = dl[i] == bt->dst_cap[i];
+        for (size_t i = 0; i < n && tight; i++)
+            tight = dl[i] == bt->dst_cap[i] && (i == 0 || bt->dst_off[i] == bt->dst_off[i - 1] + bt->dst_cap[i - 1]);
         if (tight) CUDA_TRY(cudaMemcpyAsync(hd + d_lo, c->d_dst.p, d_bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     if (!tight) {

@@ -969,6 +969,14 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         if (bt->src_len[i] > MAX_UNIT || bt->dst_cap[i] > MAX_UNIT) continue;
         if (bt->src_len[i] < (1u << 17)) continue;   // small streams: one warp is as good
         if (!lz4f_plan_host(hs + bt->src_off[i], (size_t)bt->src_len[i], frames[i], blocks[i]) || blocks[i].size() < 2) continue;
+        // Scratch is sized from untrusted block headers: a block can produce at most min(bmax, 255 x its length), and a
+        // stream whose slots would far exceed what the caller can take (many tiny blocks under a 4 MiB bmax) is decoded
+        // serially like the reference does, instead of failing with CJ_E_NOMEM.
+        size_t want = 0;
+        for (const Lz4fFrame& f : frames[i])
+            for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++)
+                if (!blocks[i][k].stored) want += cj_align16(std::min<size_t>(f.bmax, (size_t)blocks[i][k].len * 255));
+        if (want > 2 * (size_t)bt->dst_cap[i] + (1u << 20)) continue;
         par[i] = 1;
         nblk += blocks[i].size();
         nfr += frames[i].size();
@@ -980,7 +988,12 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         for (const Lz4fFrame& f : frames[i])
             for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++) {
                 const Lz4fBlock& b = blocks[i][k];
-                if (!b.stored) { dec_of.push_back(dec.size()); dec.add(sbase[i] + b.payload_off, b.len, slot_bytes, f.bmax); slot_bytes += cj_align16(f.bmax); }
+                if (!b.stored) {
+                    const size_t bslot = std::min<size_t>(f.bmax, (size_t)b.len * 255);
+                    dec_of.push_back(dec.size());
+                    dec.add(sbase[i] + b.payload_off, b.len, slot_bytes, bslot);
+                    slot_bytes += cj_align16(bslot);
+                }
                 else dec_of.push_back(~(size_t)0);
                 if (b.has_sum) { sum_of.push_back(sums.size()); sums.add(sbase[i] + b.payload_off, b.len, 0, 0); }
                 else sum_of.push_back(~(size_t)0);
@@ -1195,11 +1208,16 @@ int zstd_decompress_frames(cj_ctx* c, int where, const cj_batch* bt) {
         bool exact = false;
         if (cj_zstd_walk_host(hs + bt->src_off[i], (size_t)bt->src_len[i], &tot, &exact, &frames[i]) != CJ_OK || !exact || tot > bt->dst_cap[i]) continue;
         size_t real = 0;   // frames that are not skippable (exact == true: every one of them declares its content size)
+        uint64_t pos = 0;
+        bool fits = true;  // never hand a frame more room than the unit has left behind the frames before it
         for (const cj_frame_info& f : frames[i]) {
             uint32_t magic; memcpy(&magic, hs + bt->src_off[i] + f.offset, 4);
-            if ((magic & 0xFFFFFFF0u) != 0x184D2A50u) real++;
+            if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) continue;
+            real++;
+            if (f.content > MAX_UNIT || f.content > bt->dst_cap[i] - pos) { fits = false; break; }
+            pos += f.content;
         }
-        if (real >= 2) par[i] = 1;
+        if (real >= 2 && fits) par[i] = 1;
     }
     for (int pass = 0; pass < 2; pass++) {
         Items it;
@@ -1409,14 +1427,18 @@ int cj_lz4f_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std:
             if (bs == 0) break;
             const size_t blen = bs & 0x7FFFFFFFu;
             if (blen > n - p) return CJ_ST_TRUNCATED;
-            if (bs >> 31) frame_tot += blen;
-            else { frame_tot += std::min(bmax, blen * 255); if (!csize) *exact = false; }
+            const size_t badd = (bs >> 31) ? blen : std::min(bmax, blen * 255);
+            if (badd > SIZE_MAX / 2 - frame_tot) return CJ_ST_TOO_BIG;
+            frame_tot += badd;
+            if (!(bs >> 31) && !csize) *exact = false;
             p += blen + (bsum ? 4 : 0);
             if (p > n) return CJ_ST_TRUNCATED;
         }
         if (csum) { if (n - p < 4) return CJ_ST_TRUNCATED; p += 4; }
-        tot += csize ? (size_t)content : frame_tot;
-        if (frames) frames->push_back({frame_at, p - frame_at, csize ? (size_t)content : frame_tot, (bool)csize});
+        const uint64_t add = csize ? content : (uint64_t)frame_tot;
+        if (add > (uint64_t)SIZE_MAX - tot) return CJ_ST_TOO_BIG;   // a wrapped sum must not come out as a small bound
+        tot += (size_t)add;
+        if (frames) frames->push_back({frame_at, p - frame_at, (size_t)add, (bool)csize});
     }
     *out = tot;
     return CJ_OK;

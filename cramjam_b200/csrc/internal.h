@@ -70,30 +70,15 @@ struct Scratch {
     }
 };
 
-// Scratch of the generation-3 decode path (lz_decode3.cu): per-unit plan arrays + the descriptor arena.
-struct G3Scratch {
-    Scratch fixed_, arena_;
+// Device scratch of the thread-per-block decode path (lz_decode4.cu): work counters + the redo list.
+struct LzScratch {
+    Scratch fixed_;
     int ensure_fixed(size_t bytes) { return fixed_.ensure(bytes); }
-    int ensure_arena(size_t bytes) { return arena_.ensure(bytes); }
     void* fixed() const { return fixed_.p; }
-    void* arena() const { return arena_.p; }
-};
-// Optional view of the index kernel's output (tests / tools): device pointers, valid until the next call on the context.
-struct G3Debug {
-    bool index_only = false;
-    const uint32_t* desc_off = nullptr;
-    const uint32_t* count = nullptr;
-    const uint32_t* ulen = nullptr;
-    const uint32_t* desc = nullptr;
-    const uint32_t* rowbase = nullptr;
-    const unsigned* redo_count = nullptr;
-    unsigned long long total = 0;
 };
 namespace cj {
-// Two-kernel decode (index walk + lane state machines) for large batches; synchronises the stream once (plan read-back).
-cudaError_t launch_lz_decode3(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream, G3Debug* dbg = nullptr);
-// One thread per block (lz_decode4.cu, Snappy raw only) + the generation-2 kernel over whatever it declines.
-cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream);
+// One thread per block (lz_decode4.cu, Snappy raw and LZ4 block) + the generation-2 kernel over whatever it declines.
+cudaError_t launch_lz_decode4(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream);
 }
 
 struct cj_ctx {
@@ -108,25 +93,22 @@ struct cj_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
-    int decode_gen = 4;            // LZ4/Snappy block decode path: 2 = one warp per block, 3 = index walk + lane state machines (lz_decode3.cu), 4 = one thread per block
-                                   // (lz_decode4.cu, Snappy), the default for large batches), 5 = 4 and 2 side by side on a split batch (Snappy)
-    long g3_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
-    int g4_share = 50;             // decode_gen 5: percentage of a Snappy batch given to the thread-per-block kernel, the rest runs concurrently on generation 2
+    int decode_gen = 4;            // LZ4/Snappy block decode path: 2 = one warp per block (lz_decode.cuh), 4 = one thread per block (lz_decode4.cu), the
+                                   // default for large batches
+    long g4_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
     const unsigned* redo_ctr = nullptr;   // device counters of the most recent generation-4 launch ([1] = units handed to generation 2)
     bool redo_valid = false;
-    cudaStream_t s_aux = nullptr;  // second stream of that split
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)
     Scratch z_lit, z_enc;                                              // zstd per-warp literal buffers / encoder scratch (device)
-    G3Scratch g3;                                                      // generation-3 LZ decode: plan arrays + descriptor arena (device)
+    LzScratch g4;                                                      // thread-per-block LZ decode: counters + redo list (device)
     cj_ctx() {
         h_src.pinned = h_dst.pinned = h_desc.pinned = true;
         f_hsrc.pinned = f_hdst.pinned = f_hdesc.pinned = true;
     }
     void release_all() {
-        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc, &g3.fixed_, &g3.arena_};
+        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc, &g4.fixed_};
         for (Scratch* s : all) s->release();
     }
 };

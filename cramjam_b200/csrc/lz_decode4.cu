@@ -445,7 +445,7 @@ static cudaError_t launch_g4(const Batch& b, const G4& g, int sm_count, cudaStre
     return cudaGetLastError();
 }
 
-cudaError_t launch_lz_decode4(int codec, const Batch& b, G3Scratch& sc, int sm_count, cudaStream_t stream) {
+cudaError_t launch_lz_decode4(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream) {
     static const int depth = [] { const char* e = getenv("CJ_G4_D"); return e ? atoi(e) : CJ_G4_D; }();
     const size_t n = b.n;
     if (sc.ensure_fixed((n + 8) * 4 + 64) != 0) return cudaErrorMemoryAllocation;

@@ -62,15 +62,17 @@ struct FwdBits {
 };
 
 // Backward bit reader.  A 64-bit window of the stream is kept in registers (two aligned 8-byte loads + a funnel
-// shift per refill, every ~40-56 consumed bits); a read is a shift and a mask.  The aligned loads may touch up to
-// 15 bytes around the stream but never leave the 16-byte-padded source unit; those bits are never used.
+// shift per refill, every ~40-56 consumed bits); a read is a shift and a mask.  Only aligned words that hold at least
+// one byte of the stream are loaded (CJ_DEVICE callers need not pad their units), the surplus bits are never used.
 struct BackBits {
     const uint8_t* p;
+    const uint8_t* e;   // one past the stream's last byte
     int32_t pos;   // bits still unread (may go negative = over-read)
     int32_t wbit;  // stream bit index of win's bit 0 (multiple of 8)
     uint64_t win;
     __device__ __forceinline__ bool init(const uint8_t* p_, uint32_t n_) {
         p = p_;
+        e = p_ + n_;
         win = 0;
         pos = 0;
         wbit = 0;
@@ -87,7 +89,7 @@ struct BackBits {
         const uint8_t* a = p + wb;
         const uint64_t* a8 = reinterpret_cast<const uint64_t*>((uintptr_t)a & ~(uintptr_t)7);
         const uint32_t sh = (uint32_t)((uintptr_t)a & 7) * 8;
-        const uint64_t lo = __ldg(a8), hi = __ldg(a8 + 1);
+        const uint64_t lo = __ldg(a8), hi = (sh && reinterpret_cast<const uint8_t*>(a8 + 1) < e) ? __ldg(a8 + 1) : 0ull;
         win = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
         wbit = wb * 8;
     }
@@ -740,14 +742,18 @@ int cj_zstd_walk_host(const uint8_t* s, size_t n, size_t* out, bool* exact, std:
             if (type == 3) return CJ_ST_CORRUPT;
             const size_t in_sz = type == 1 ? 1 : bsz;
             if (in_sz > n - q) return CJ_ST_TRUNCATED;
+            if ((type == 2 ? bmax : (size_t)bsz) > SIZE_MAX / 2 - frame_tot) return CJ_ST_TOO_BIG;
             frame_tot += type == 2 ? bmax : bsz;
             q += in_sz;
             if (bh & 1) break;
         }
         if (fhd & 4) { if (n - q < 4) return CJ_ST_TRUNCATED; q += 4; }
-        if (fsz) tot += (size_t)fcs;
-        else { tot += frame_tot; *exact = false; }
-        if (frames) frames->push_back({p, q - p, fsz ? (size_t)fcs : frame_tot, fsz != 0});
+        // untrusted 64-bit content sizes: a sum that wraps must not come out as a small bound
+        const uint64_t add = fsz ? fcs : (uint64_t)frame_tot;
+        if (add > (uint64_t)SIZE_MAX - tot) return CJ_ST_TOO_BIG;
+        tot += (size_t)add;
+        if (!fsz) *exact = false;
+        if (frames) frames->push_back({p, q - p, (size_t)add, fsz != 0});
         p = q;
     }
     *out = tot;

@@ -264,13 +264,27 @@ static size_t opt_size(const py::object& o) { return o.is_none() ? SIZE_MAX : o.
 static py::object make_buffer(Bytes v) { return py::cast(new Buffer(std::move(v)), py::return_value_policy::take_ownership); }
 
 // ---- the generic compress / decompress / *_into quartet shared by the three variants ----
-static py::object generic_compress(cj_codec codec, py::handle data, int level) {
+// `output_len` is a size hint in the reference, not a capacity: generic! builds `vec![0; len]` and writes through a
+// Cursor over that Vec, which grows (src/lib.rs:217-233).  The result is therefore max(len, produced) bytes long, zero
+// padded behind what was produced, and an undersized hint still succeeds.
+static void pad_to_hint(Bytes& v, size_t hint) {
+    if (hint != SIZE_MAX && hint > v.size()) {
+        const size_t old = v.size();
+        v.resize(hint);
+        std::memset(v.data() + old, 0, hint - old);
+    }
+}
+static py::object generic_compress(cj_codec codec, py::handle data, int level, const py::object& output_len = py::none()) {
     Input in(data);
-    return make_buffer(do_compress(codec, in.p, in.n, level));
+    Bytes out = do_compress(codec, in.p, in.n, level);
+    pad_to_hint(out, opt_size(output_len));
+    return make_buffer(std::move(out));
 }
 static py::object generic_decompress(cj_codec codec, py::handle data, const py::object& output_len) {
     Input in(data);
-    return make_buffer(do_decompress(codec, in.p, in.n, opt_size(output_len)));
+    Bytes out = do_decompress(codec, in.p, in.n, SIZE_MAX);
+    pad_to_hint(out, opt_size(output_len));
+    return make_buffer(std::move(out));
 }
 static size_t generic_compress_into(cj_codec codec, py::handle input, py::handle output, int level) {
     Input in(input);
@@ -617,7 +631,7 @@ PYBIND11_MODULE(cramjam, m) {
     // ------------------------------------------------------------------ snappy (src/snappy.rs)
     {
         auto s = m.def_submodule("snappy", "snappy de/compression interface");
-        s.def("compress", [](py::handle data, py::object) { return generic_compress(CJ_SNAPPY_FRAMED, data, -1); }, py::arg("data"), py::arg("output_len") = py::none());
+        s.def("compress", [](py::handle data, py::object output_len) { return generic_compress(CJ_SNAPPY_FRAMED, data, -1, output_len); }, py::arg("data"), py::arg("output_len") = py::none());
         s.def("decompress", [](py::handle data, py::object output_len) { return generic_decompress(CJ_SNAPPY_FRAMED, data, output_len); }, py::arg("data"),
               py::arg("output_len") = py::none());
         s.def("compress_into", [](py::handle input, py::handle output) { return generic_compress_into(CJ_SNAPPY_FRAMED, input, output, -1); }, py::arg("input"), py::arg("output"));
@@ -655,7 +669,7 @@ PYBIND11_MODULE(cramjam, m) {
     {
         auto l = m.def_submodule("lz4", "LZ4 de/compression interface");
         auto lvl = [](const py::object& o) { return o.is_none() ? 4 : o.cast<int>(); };  // DEFAULT_COMPRESSION_LEVEL = 4 (src/lz4.rs:17)
-        l.def("compress", [lvl](py::handle data, py::object level, py::object) { return generic_compress(CJ_LZ4_FRAME, data, lvl(level)); }, py::arg("data"),
+        l.def("compress", [lvl](py::handle data, py::object level, py::object output_len) { return generic_compress(CJ_LZ4_FRAME, data, lvl(level), output_len); }, py::arg("data"),
               py::arg("level") = py::none(), py::arg("output_len") = py::none());
         l.def("decompress", [](py::handle data, py::object output_len) { return generic_decompress(CJ_LZ4_FRAME, data, output_len); }, py::arg("data"),
               py::arg("output_len") = py::none());
@@ -728,7 +742,7 @@ PYBIND11_MODULE(cramjam, m) {
     {
         auto z = m.def_submodule("zstd", "zstd de/compression interface");
         auto lvl = [](const py::object& o) { return o.is_none() ? 0 : o.cast<int>(); };  // DEFAULT_COMPRESSION_LEVEL = 0 -> libzstd default (src/zstd.rs:14)
-        z.def("compress", [lvl](py::handle data, py::object level, py::object) { return generic_compress(CJ_ZSTD, data, lvl(level)); }, py::arg("data"),
+        z.def("compress", [lvl](py::handle data, py::object level, py::object output_len) { return generic_compress(CJ_ZSTD, data, lvl(level), output_len); }, py::arg("data"),
               py::arg("level") = py::none(), py::arg("output_len") = py::none());
         z.def("decompress", [](py::handle data, py::object output_len) { return generic_decompress(CJ_ZSTD, data, output_len); }, py::arg("data"),
               py::arg("output_len") = py::none());

@@ -63,6 +63,21 @@ def test_simple(cj, variant, is_bytearray):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_output_len_is_a_hint(cj, variant):
+    # generic! builds vec![0; output_len] and writes through a growing Cursor (src/lib.rs:217-233): an undersized hint
+    # still succeeds, an oversized one returns max(hint, produced) bytes, zero padded
+    mod = getattr(cj, variant)
+    raw = corpus.text(5000, 3)
+    comp = bytes(mod.compress(raw))
+    assert bytes(mod.decompress(comp, output_len=10)) == raw
+    big = bytes(mod.decompress(comp, output_len=len(raw) + 100))
+    assert big[:len(raw)] == raw and big[len(raw):] == b"\x00" * 100
+    padded = bytes(mod.compress(raw, output_len=len(comp) + 50))
+    assert padded[:len(comp)] == comp and padded[len(comp):] == b"\x00" * 50
+    assert bytes(mod.compress(raw, output_len=3)) == comp
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_raises(cj, variant):
     with pytest.raises(cj.DecompressionError):
         getattr(cj, variant).decompress(b"sknow")

@@ -1,7 +1,6 @@
-"""-m gpu parity tests of the alternative block-decode paths — generation 3 (lz_decode3.cu: index walk + lane state
-machines), generation 4 (lz_decode4.cu: one thread per block) and 5 (4 and 2 side by side on a split batch), each with
-the generation-2 redo list — forced on through cj_ctx_set_decode_path() for every batch size.
-Same oracle, same status-code expectations as test_gpu_lz_decode.py."""
+"""-m gpu parity tests of the thread-per-block decode path (generation 4, lz_decode4.cu: Snappy raw and LZ4 block) with
+its generation-2 redo list, forced on through cj_ctx_set_decode_path() for every batch size, and of batches beyond one
+wave of the kernel (the multi-round path).  Same oracle, same status-code expectations as test_gpu_lz_decode.py."""
 import numpy as np
 import pytest
 
@@ -17,10 +16,10 @@ pytestmark = pytest.mark.gpu
 CASES = corpus.edge_cases()
 
 
-@pytest.fixture(autouse=True, params=[3, 4, 5], ids=["gen3", "gen4", "gen5"])
-def gen3(request):
+@pytest.fixture(autouse=True)
+def gen4():
     default = ctx().decode_path()
-    ctx().set_decode_path(request.param, 1)   # generations 4 and 5 take Snappy only; LZ4 batches stay on generation 2
+    ctx().set_decode_path(4, 1)
     yield
     ctx().set_decode_path(*default)
 
@@ -105,3 +104,43 @@ def test_long_literals_and_long_matches():
     for codec, comp in ((capi.SNAPPY_RAW, O.snappy_raw_compress), (capi.LZ4_BLOCK, O.lz4_block_compress)):
         units = [comp(d) for d in datas]
         assert_same_as_oracle(codec, units, [len(d) for d in datas], "device")
+
+
+@pytest.mark.parametrize("codec", [capi.SNAPPY_RAW, capi.LZ4_BLOCK])
+def test_multi_round_batch_configs4_size(codec):
+    """131 072 x 64 KiB blocks per GPU (BASELINE.json configs[4] per-GPU size) is more than one wave of the
+    thread-per-block kernel (148 SMs x 20 warps x 32 lanes = 94 720 blocks): the batch is decoded in several rounds.
+    A 4 096-block sample is encoded by the ORACLE encoder (not the GPU encoder); the batch tiles the sample's
+    descriptors 32 times (indices, not bytes) into 131 072 distinct output slots, and every slot must equal the
+    generator's original block."""
+    import torch
+    S_, U, REP = 4096, 65536, 32
+    n = S_ * REP
+    data = capi.synth_host(S_, U, seed=0xC0FFEE, first_index=7000)
+    bound = lambda k: (32 + k + k // 6) if codec == capi.SNAPPY_RAW else (k + k // 255 + 16)
+    slot = (bound(U) + 15) // 16 * 16
+    src = np.zeros(S_ * slot + 64, dtype=np.uint8)
+    so1 = np.arange(S_, dtype=np.uint64) * np.uint64(U)
+    do1 = np.arange(S_, dtype=np.uint64) * np.uint64(slot)
+    lens = O.batch(O.SNAPPY_RAW if codec == capi.SNAPPY_RAW else O.LZ4_BLOCK, 1, data, so1, np.full(S_, U, dtype=np.uint64), src, do1,
+                   np.full(S_, slot, dtype=np.uint64), nthreads=16)[0]
+    assert (lens > 0).all()
+    dev = torch.device("cuda:0")
+    as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(dev)
+    t_src = torch.from_numpy(src).to(dev)
+    t_so = as_i64(np.tile(do1, REP))
+    t_sl = as_i64(np.tile(lens.astype(np.uint64), REP))
+    t_do = as_i64(np.arange(n, dtype=np.uint64) * np.uint64(U))
+    t_dc = as_i64(np.full(n, U, dtype=np.uint64))
+    t_dl = torch.zeros(n, dtype=torch.int64, device=dev)
+    t_st = torch.full((n,), -99, dtype=torch.int32, device=dev)
+    t_dst = torch.zeros(n * U + 64, dtype=torch.uint8, device=dev)
+    c = ctx()
+    c.decompress_batch(codec, capi.DEVICE, n, t_src, t_so, t_sl, t_dst, t_do, t_dc, t_dl, t_st)
+    c.synchronize()
+    assert int((t_st != 0).sum()) == 0 and int((t_dl != U).sum()) == 0
+    assert c.last_redo_count() == 0
+    want = torch.from_numpy(data).to(dev)
+    got = t_dst[:n * U].view(REP, S_ * U)
+    for r in range(REP):
+        assert torch.equal(got[r], want), r
