@@ -3,8 +3,9 @@
 Every unit (snappy raw block / LZ4 block / frame) is independent, so the batch is cut into contiguous
 ranges of the unit index space, one per rank, balanced by uncompressed bytes.  No collective is needed
 when each rank generates or already holds its range (bench.py's mode).  For the "batch lives on rank 0"
-mode, `scatter_units` / `gather_units` move the ranges with point-to-point sends over torch.distributed
-(NCCL over NVLink on GPUs; gloo in the CPU tests) — a trivial exchange, no reduction.
+mode, a `ShardPlan` (one descriptor broadcast, made before the timed path) says which contiguous span of rank 0's arena
+every rank decodes; `scatter_payload` / `gather_payload` then move those spans as one batched point-to-point group over
+torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests) — a trivial exchange, no reduction, no host round trip.
 """
 from typing import Callable, List, Sequence, Tuple
 
@@ -39,94 +40,122 @@ def _dist():
     return dist
 
 
-def scatter_units(payload, offsets: np.ndarray, lengths: np.ndarray, ranges: List[Tuple[int, int]], src_rank: int = 0, device=None):
-    """Rank `src_rank` holds `payload` (1-D uint8 tensor) with unit i at [offsets[i], offsets[i]+lengths[i]).
-    Returns (local_payload, local_offsets, local_lengths) for this rank's range.  Descriptors travel as one
-    broadcast; payload ranges as point-to-point sends (ranges are contiguous spans of the arena)."""
+class ShardPlan:
+    """Everything the payload moves need, known on every rank before the timed path: the unit ranges per rank and every
+    unit's offset / length inside the source rank's input arena and inside the gathered output."""
+
+    def __init__(self, ranges, in_off, in_len, out_len, src_rank):
+        self.ranges, self.src_rank = ranges, src_rank
+        self.in_off, self.in_len, self.out_len = in_off, in_len, out_len
+        n = len(out_len)
+        self.out_off = np.zeros(n, dtype=np.uint64)
+        if n:
+            self.out_off[1:] = np.cumsum(out_len[:-1])
+
+    def count(self, r):
+        return self.ranges[r][1] - self.ranges[r][0]
+
+    def in_span(self, r):
+        s, e = self.ranges[r]
+        return (0, 0) if s == e else (int(self.in_off[s]), int(self.in_off[e - 1] + self.in_len[e - 1]))
+
+    def in_bytes(self, r):
+        a, b = self.in_span(r)
+        return b - a
+
+    def out_span(self, r):
+        s, e = self.ranges[r]
+        return (0, 0) if s == e else (int(self.out_off[s]), int(self.out_off[e - 1] + self.out_len[e - 1]))
+
+    def local_offsets(self, r):
+        s, e = self.ranges[r]
+        return self.in_off[s:e] - np.uint64(self.in_span(r)[0])
+
+    def local_lengths(self, r):
+        s, e = self.ranges[r]
+        return self.in_len[s:e]
+
+
+def make_plan(offsets, lengths, out_lengths, weights, src_rank: int = 0, device=None) -> ShardPlan:
+    """One broadcast of a packed int64 tensor [n | offsets | lengths | out_lengths] from `src_rank` (the other ranks pass
+    None for the three arrays); `weights` (same on every rank, e.g. uncompressed bytes per unit) decides the ranges."""
     import torch
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
-    device = device if device is not None else (payload.device if payload is not None else torch.device("cpu"))
-    n_t = torch.zeros(1, dtype=torch.int64, device=device)
+    device = device if device is not None else torch.device("cpu")
+    n = len(weights)
+    desc = torch.zeros(3 * n, dtype=torch.int64, device=device)
     if rank == src_rank:
-        n_t[0] = len(offsets)
-    dist.broadcast(n_t, src_rank)
-    n = int(n_t.item())
-    desc = torch.zeros(2 * n, dtype=torch.int64, device=device)
-    if rank == src_rank:
-        desc[:n] = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64)).to(device)
-        desc[n:] = torch.from_numpy(np.ascontiguousarray(lengths, dtype=np.int64)).to(device)
+        host = np.concatenate([np.ascontiguousarray(a, dtype=np.uint64).view(np.int64) for a in (offsets, lengths, out_lengths)])
+        desc.copy_(torch.from_numpy(host))
     dist.broadcast(desc, src_rank)
-    off = desc[:n].cpu().numpy().astype(np.uint64)
-    ln = desc[n:].cpu().numpy().astype(np.uint64)
-
-    def span(r):
-        s, e = ranges[r]
-        if s == e:
-            return 0, 0
-        return int(off[s]), int(off[e - 1] + ln[e - 1])
-
-    s, e = ranges[rank]
-    lo, hi = span(rank)
-    local = torch.empty(hi - lo, dtype=torch.uint8, device=device)
-    if rank == src_rank:
-        reqs = []
-        for r in range(world):
-            a, b = span(r)
-            if r == rank:
-                local.copy_(payload[a:b])
-            elif b > a:
-                reqs.append(dist.isend(payload[a:b].contiguous(), r))
-        for q in reqs:
-            q.wait()
-    elif hi > lo:
-        dist.recv(local, src_rank)
-    return local, (off[s:e] - np.uint64(lo)), ln[s:e]
+    h = desc.cpu().numpy().view(np.uint64)
+    return ShardPlan(partition_units(weights, world), h[:n].copy(), h[n:2 * n].copy(), h[2 * n:].copy(), src_rank)
 
 
-def gather_units(local_out, local_lengths: np.ndarray, ranges: List[Tuple[int, int]], dst_rank: int = 0):
-    """Inverse of scatter_units for the outputs: every rank sends its densely packed output bytes to `dst_rank`,
-    which returns (payload, offsets, lengths) in global unit order; other ranks return None."""
-    import torch
+def scatter_payload(plan: ShardPlan, payload, local):
+    """Moves every rank's contiguous span of the source arena into its `local` tensor: all sends and receives of the step
+    are posted as one batched point-to-point group (one NCCL group on GPUs), nothing touches the host."""
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
-    device = local_out.device
-    n_total = ranges[-1][1]
-    lens = torch.zeros(n_total, dtype=torch.int64, device=device)
-    s, e = ranges[rank]
-    if e > s:
-        lens[s:e] = torch.from_numpy(np.ascontiguousarray(local_lengths, dtype=np.int64)).to(device)
-    dist.all_reduce(lens)  # disjoint ranges: the sum is the concatenation
-    ln = lens.cpu().numpy().astype(np.uint64)
-    off = np.zeros(n_total, dtype=np.uint64)
-    if n_total:
-        off[1:] = np.cumsum(ln[:-1])
-    total = int(ln.sum())
-    sizes = [int(ln[a:b].sum()) for a, b in ranges]
-    if rank == dst_rank:
-        out = torch.empty(total, dtype=torch.uint8, device=device)
-        pos = [int(off[a]) if b > a else 0 for a, b in ranges]
-        reqs = []
+    ops = []
+    if rank == plan.src_rank:
         for r in range(world):
-            if sizes[r] == 0:
+            a, b = plan.in_span(r)
+            if b <= a:
                 continue
             if r == rank:
-                out[pos[r]:pos[r] + sizes[r]].copy_(local_out[:sizes[r]])
+                local[: b - a].copy_(payload[a:b])
             else:
-                reqs.append(dist.irecv(out[pos[r]:pos[r] + sizes[r]], r))
-        for q in reqs:
+                ops.append(dist.P2POp(dist.isend, payload[a:b], r))
+    else:
+        a, b = plan.in_span(rank)
+        if b > a:
+            ops.append(dist.P2POp(dist.irecv, local[: b - a], plan.src_rank))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
-        return out, off, ln
-    if sizes[rank]:
-        dist.send(local_out[:sizes[rank]].contiguous(), dst_rank)
-    return None
 
 
-def run_sharded(payload, offsets, lengths, weights, codec_fn: Callable, src_rank: int = 0, device=None):
-    """scatter -> per-rank codec_fn(local_payload, local_offsets, local_lengths) -> gather.
-    codec_fn returns (dense_output_tensor, output_lengths)."""
+def gather_payload(plan: ShardPlan, local_out, gathered):
+    """Inverse move for the outputs (their lengths are part of the plan): every rank's dense output lands at its place in
+    `gathered` on the source rank, again as one batched group."""
     dist = _dist()
-    ranges = partition_units(weights, dist.get_world_size())
-    local, loff, llen = scatter_units(payload, offsets, lengths, ranges, src_rank, device)
-    out, out_len = codec_fn(local, loff, llen)
-    return gather_units(out, out_len, ranges, src_rank)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    if rank == plan.src_rank:
+        for r in range(world):
+            a, b = plan.out_span(r)
+            if b <= a:
+                continue
+            if r == rank:
+                gathered[a:b].copy_(local_out[: b - a])
+            else:
+                ops.append(dist.P2POp(dist.irecv, gathered[a:b], r))
+    else:
+        a, b = plan.out_span(rank)
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, local_out[: b - a], plan.src_rank))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+
+
+def run_sharded(payload, offsets, lengths, out_lengths, codec_fn: Callable, src_rank: int = 0, device=None):
+    """plan -> scatter -> per-rank codec_fn(local_payload, local_offsets, local_lengths, local_out_lengths) -> gather.
+    `out_lengths` (known on every rank: for decompression the units' uncompressed sizes) also balances the ranges;
+    codec_fn returns this rank's densely packed output tensor.  Returns (gathered, out_offsets, out_lengths) on
+    `src_rank`, None elsewhere."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank()
+    device = device if device is not None else torch.device("cpu")
+    out_lengths = np.ascontiguousarray(out_lengths, dtype=np.uint64)
+    plan = make_plan(offsets, lengths, out_lengths, out_lengths, src_rank, device)
+    local = torch.empty(max(plan.in_bytes(rank), 1), dtype=torch.uint8, device=device)
+    scatter_payload(plan, payload, local)
+    s, e = plan.ranges[rank]
+    out = codec_fn(local[: plan.in_bytes(rank)], plan.local_offsets(rank), plan.local_lengths(rank), out_lengths[s:e])
+    gathered = torch.empty(int(out_lengths.sum()), dtype=torch.uint8, device=device) if rank == src_rank else None
+    gather_payload(plan, out, gathered)
+    return (gathered, plan.out_off, plan.out_len) if rank == src_rank else None

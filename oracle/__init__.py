@@ -27,6 +27,80 @@ def build(force=False):
     return _SO
 
 
+_STANDIN_SO = os.path.join(_DIR, "libcj_standin.so")
+_standin = None
+
+
+def build_standin(force=False):
+    """Builds the stand-in harness (standin.cpp over pyarrow's bundled Google snappy / lz4 / zstd).  Returns the path,
+    or None when pyarrow (its headers or libarrow) is not there."""
+    src = os.path.join(_DIR, "standin.cpp")
+    if not force and os.path.exists(_STANDIN_SO) and os.path.getmtime(_STANDIN_SO) >= os.path.getmtime(src):
+        return _STANDIN_SO
+    try:
+        import glob
+        import pyarrow
+        inc = pyarrow.get_include()
+        libs = sorted(glob.glob(os.path.join(os.path.dirname(pyarrow.__file__), "libarrow.so*")))
+        if not libs or not os.path.exists(os.path.join(inc, "arrow", "util", "compression.h")):
+            return None
+        subprocess.check_call(["make", "-C", _DIR, "-s", "libcj_standin.so", f"ARROW_INC={inc}", f"ARROW_LIB={libs[0]}"])
+        return _STANDIN_SO
+    except Exception:
+        return None
+
+
+def standin():
+    """The stand-in library or None.  Only bench.py's CPU legs and tests use it."""
+    global _standin
+    if _standin is None:
+        so = build_standin()
+        if so is None:
+            _standin = False
+        else:
+            try:
+                L = C.CDLL(so)
+                u8p, sz = C.c_void_p, C.c_size_t
+                L.cjs_batch.argtypes = [C.c_int, C.c_int, C.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p, u8p, C.c_int, C.POINTER(C.c_double)]
+                L.cjs_batch.restype = C.c_int
+                L.cjs_describe.restype = C.c_char_p
+                _standin = L
+            except OSError:
+                _standin = False
+    return _standin or None
+
+
+def standin_batch(codec, direction, src_base, src_off, src_len, dst_base, dst_off, dst_cap, nthreads=1, level=3):
+    """Same contract as batch() over the stand-in libraries; out_len[i] = -1 where a unit failed.  None if unavailable."""
+    L = standin()
+    if L is None:
+        return None
+    n = len(src_off)
+    so = np.ascontiguousarray(src_off, dtype=np.uint64); sl = np.ascontiguousarray(src_len, dtype=np.uint64)
+    do = np.ascontiguousarray(dst_off, dtype=np.uint64); dc = np.ascontiguousarray(dst_cap, dtype=np.uint64)
+    out = np.empty(n, dtype=np.int64)
+    sec = C.c_double(0)
+    rc = L.cjs_batch(codec, direction, level, n, src_base.ctypes.data, so.ctypes.data, sl.ctypes.data,
+                     dst_base.ctypes.data, do.ctypes.data, dc.ctypes.data, out.ctypes.data, nthreads, C.byref(sec))
+    if rc != 0:
+        return None
+    return out, sec.value
+
+
+def pack_units(src, src_off, lens, dst, dst_off, nthreads=1):
+    """dst[dst_off[i] : +lens[i]] = src[src_off[i] : +lens[i]] for every unit (benchmark set-up helper)."""
+    so = np.ascontiguousarray(src_off, dtype=np.uint64); ln = np.ascontiguousarray(lens, dtype=np.uint64)
+    do = np.ascontiguousarray(dst_off, dtype=np.uint64)
+    lib().cjo_pack_units(src.ctypes.data, so.ctypes.data, ln.ctypes.data, dst.ctypes.data, do.ctypes.data, len(ln), nthreads)
+
+
+def synth(n_blocks, block_len, seed=0xC0FFEE, first_index=0, nthreads=None):
+    """The synthetic corpus (oracle/synth.c), identical bytes to cramjam_b200's device / host generator."""
+    out = np.empty(n_blocks * block_len, dtype=np.uint8)
+    lib().cjo_synth_blocks(out.ctypes.data, n_blocks, block_len, seed, first_index, nthreads or (os.cpu_count() or 1))
+    return out
+
+
 _lib = None
 
 
@@ -62,6 +136,10 @@ def lib():
         L.cjo_xxh64.argtypes = [u8p, sz, C.c_uint64]; L.cjo_xxh64.restype = C.c_uint64
         L.cjo_batch.argtypes = [C.c_int, C.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p, u8p, C.c_int, C.POINTER(C.c_double)]
         L.cjo_batch.restype = C.c_int
+        L.cjo_synth_blocks.argtypes = [u8p, sz, sz, C.c_uint64, C.c_uint64, C.c_int]
+        L.cjo_synth_blocks.restype = None
+        L.cjo_pack_units.argtypes = [u8p, u8p, u8p, u8p, u8p, sz, C.c_int]
+        L.cjo_pack_units.restype = None
         _lib = L
     return _lib
 

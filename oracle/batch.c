@@ -77,3 +77,28 @@ int cjo_batch(int codec, int dir, size_t n, const uint8_t* src_base, const uint6
 }
 
 const char* cjo_version(void) { return "cj_oracle 0.1 (snappy raw/framed, lz4 block/frame, zstd decode)"; }
+
+/* ---- dense packing of units (set-up of the benchmark arenas, untimed): dst[do[i]..] = src[so[i] .. so[i]+len[i]) ---- */
+#include <string.h>
+typedef struct { const uint8_t* src; const uint64_t* so; const uint64_t* len; uint8_t* dst; const uint64_t* dof; size_t n, next; } pjob_t;
+static void* pworker(void* arg) {
+    pjob_t* j = (pjob_t*)arg;
+    for (;;) {
+        size_t i = __atomic_fetch_add(&j->next, 64, __ATOMIC_RELAXED);
+        if (i >= j->n) break;
+        size_t e = i + 64 < j->n ? i + 64 : j->n;
+        for (; i < e; i++) memcpy(j->dst + j->dof[i], j->src + j->so[i], (size_t)j->len[i]);
+    }
+    return NULL;
+}
+void cjo_pack_units(const uint8_t* src, const uint64_t* so, const uint64_t* len, uint8_t* dst, const uint64_t* dof, size_t n, int nthreads) {
+    pjob_t j = {src, so, len, dst, dof, n, 0};
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    pthread_t th[64];
+    int started = 0;
+    for (int t = 1; t < nthreads; t++)
+        if (pthread_create(&th[started], NULL, pworker, &j) == 0) started++;
+    pworker(&j);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}

@@ -100,6 +100,12 @@ int cjo_batch(int codec, int dir, size_t n,
               uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* dst_cap,
               int64_t* out_len, int nthreads, double* seconds);
 
+/* ---- the synthetic corpus of SURVEY.md 8(d) for the CPU arms (synth.c; identical bytes to the device generator) */
+void cjo_synth_block(uint8_t* out, size_t len, uint64_t seed, uint64_t index);
+void cjo_synth_blocks(uint8_t* out, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index, int nthreads);
+
+void cjo_pack_units(const uint8_t* src, const uint64_t* so, const uint64_t* len, uint8_t* dst, const uint64_t* dof, size_t n, int nthreads);
+
 const char* cjo_version(void);
 
 #ifdef __cplusplus

@@ -55,15 +55,16 @@ def _worker(rank, world, port, q):
             payload = torch.from_numpy(np.frombuffer(b"".join(blocks), dtype=np.uint8).copy())
         weights = np.full(n, U)
 
-        def codec(local, loff, llen):
+        def codec(local, loff, llen, lout):
             src = local.numpy()
             k = len(loff)
+            assert (lout == U).all()
             dst = np.zeros(k * U, dtype=np.uint8)
             do = np.arange(k, dtype=np.uint64) * U
             out_len, _ = O.batch(O.SNAPPY_RAW, 0, src if src.size else np.zeros(1, np.uint8), loff, llen, dst if k else np.zeros(1, np.uint8), do,
                                  np.full(k, U, np.uint64), nthreads=2)
             assert (out_len == U).all()
-            return torch.from_numpy(dst), out_len.astype(np.uint64)
+            return torch.from_numpy(dst)
 
         res = run_sharded(payload, offsets, lengths, weights, codec, src_rank=0, device=torch.device("cpu"))
         if rank == 0:
