@@ -976,7 +976,7 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         for (const Lz4fFrame& f : frames[i])
             for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++)
                 if (!blocks[i][k].stored) want += cj_align16(std::min<size_t>(f.bmax, (size_t)blocks[i][k].len * 255));
-        if (want > 2 * (size_t)bt->dst_cap[i] + (1u << 20)) continue;
+        if (want > 16 * (size_t)bt->dst_cap[i] + ((size_t)64 << 20)) continue;
         par[i] = 1;
         nblk += blocks[i].size();
         nfr += frames[i].size();

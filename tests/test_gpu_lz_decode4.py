@@ -136,6 +136,7 @@ def test_multi_round_batch_configs4_size(codec):
     t_st = torch.full((n,), -99, dtype=torch.int32, device=dev)
     t_dst = torch.zeros(n * U + 64, dtype=torch.uint8, device=dev)
     c = ctx()
+    torch.cuda.synchronize()   # the context runs on its own stream: the tensors above must exist before it starts
     c.decompress_batch(codec, capi.DEVICE, n, t_src, t_so, t_sl, t_dst, t_do, t_dc, t_dl, t_st)
     c.synchronize()
     assert int((t_st != 0).sum()) == 0 and int((t_dl != U).sum()) == 0

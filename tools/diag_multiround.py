@@ -33,7 +33,7 @@ c = capi.Context(0)
 for gen in (4, 2):
     c.set_decode_path(gen, 1)
     for rep in range(reps):
-        t_dst.fill_(0xEE)
+        t_dst.fill_(0xEE); t_st.fill_(-99); torch.cuda.synchronize()
         c.decompress_batch(codec, capi.DEVICE, n, t_src, t_so, t_sl, t_dst, t_do, t_dc, t_dl, t_st)
         c.synchronize()
         got = t_dst[:n * U].view(REP, S_, U)
