@@ -68,6 +68,10 @@ def lib():
         "cj_compress_batch": ([vp, C.c_int, C.c_int, C.POINTER(Batch), C.POINTER(Params)], C.c_int),
         "cj_decompress": ([vp, C.c_int, vp, sz, vp, sz, C.POINTER(sz)], C.c_int),
         "cj_compress": ([vp, C.c_int, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Params)], C.c_int),
+        "cj_decompress_ex": ([vp, C.c_int, C.c_int, vp, sz, vp, sz, C.POINTER(sz)], C.c_int),
+        "cj_compress_ex": ([vp, C.c_int, C.c_int, vp, sz, vp, sz, C.POINTER(sz), C.POINTER(Params)], C.c_int),
+        "cj_host_register": ([vp, vp, sz], C.c_int),
+        "cj_host_unregister": ([vp, vp], C.c_int),
         "cj_synth_blocks": ([vp, C.c_int, vp, sz, sz, u64, u64], C.c_int),
         "cj_copy_units": ([vp, sz, vp, vp, vp, vp, vp], C.c_int),
         "cj_device_alloc": ([vp, sz, C.POINTER(vp)], C.c_int),

@@ -526,7 +526,7 @@ int cj_compress_batch(cj_ctx* c, cj_codec codec, cj_mem where, const cj_batch* b
 }
 
 static int single(cj_ctx* c, cj_codec codec, bool compress, const void* src, size_t n, void* dst, size_t cap, size_t* written,
-                  const cj_params* params) {
+                  const cj_params* params, int where = CJ_HOST) {
     uint64_t so = 0, sl = n, dof = 0, dc = cap, dl = 0;
     int32_t st = 0;
     static uint8_t dummy[16];
@@ -535,8 +535,32 @@ static int single(cj_ctx* c, cj_codec codec, bool compress, const void* src, siz
     b.src_base = src ? src : dummy; b.src_off = &so; b.src_len = &sl;
     b.dst_base = dst ? dst : dummy; b.dst_off = &dof; b.dst_cap = &dc;
     b.dst_len = &dl; b.status = &st;
-    int rc = run_batch(c, (int)codec, compress, CJ_HOST, &b, params);
-    if (rc) return rc;
+    int rc;
+    if (where == CJ_DEVICE) {
+        // device-resident pair: the six descriptor words travel through a small device scratch of their own
+        if (!c) { cj_set_error("null context"); return CJ_E_INVALID_ARG; }
+        if (!src || !dst) { cj_set_error("null device pointer"); return CJ_E_INVALID_ARG; }
+        uint64_t h[6] = {so, sl, dof, dc, 0, 0};
+        std::lock_guard<std::mutex> one(c->mu_one);   // the scratch is this call's from upload to read-back
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            CUDA_TRY(cudaSetDevice(c->device));
+            if ((rc = c->d_one.ensure(64))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->d_one.p, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+        }
+        uint64_t* d = (uint64_t*)c->d_one.p;
+        b.src_off = d; b.src_len = d + 1; b.dst_off = d + 2; b.dst_cap = d + 3; b.dst_len = d + 4; b.status = (int32_t*)(d + 5);
+        rc = run_batch(c, (int)codec, compress, CJ_DEVICE, &b, params);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> g(c->mu);
+        CUDA_TRY(cudaMemcpyAsync(h + 4, d + 4, 16, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        dl = h[4];
+        st = (int32_t)(h[5] & 0xFFFFFFFFu);
+    } else {
+        rc = run_batch(c, (int)codec, compress, where, &b, params);
+        if (rc) return rc;
+    }
     if (written) *written = (size_t)dl;
     if (st != CJ_OK) {
         cj_set_error("%s", cj_status_string(st));
@@ -551,6 +575,15 @@ int cj_decompress(cj_ctx* c, cj_codec codec, const void* src, size_t n, void* ds
 
 int cj_compress(cj_ctx* c, cj_codec codec, const void* src, size_t n, void* dst, size_t cap, size_t* written, const cj_params* params) {
     return single(c, codec, true, src, n, dst, cap, written, params);
+}
+
+int cj_decompress_ex(cj_ctx* c, cj_codec codec, cj_mem where, const void* src, size_t n, void* dst, size_t cap, size_t* written) {
+    return single(c, codec, false, src, n, dst, cap, written, nullptr, (int)where);
+}
+
+int cj_compress_ex(cj_ctx* c, cj_codec codec, cj_mem where, const void* src, size_t n, void* dst, size_t cap, size_t* written,
+                   const cj_params* params) {
+    return single(c, codec, true, src, n, dst, cap, written, params, (int)where);
 }
 
 int cj_synth_blocks(cj_ctx* c, cj_mem where, void* dst, size_t n_blocks, size_t block_len, uint64_t seed, uint64_t first_index) {
@@ -604,6 +637,19 @@ int cj_pinned_alloc(cj_ctx* c, size_t bytes, void** out) {
 int cj_pinned_free(cj_ctx* c, void* p) {
     if (!c) return CJ_E_INVALID_ARG;
     CUDA_TRY(cudaFreeHost(p));
+    return CJ_OK;
+}
+int cj_host_register(cj_ctx* c, void* p, size_t bytes) {
+    if (!c || !p || !bytes) return CJ_E_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); cj_set_error("cudaHostRegister(%zu) failed: %s", bytes, cudaGetErrorString(e)); return CJ_E_CUDA; }
+    return CJ_OK;
+}
+int cj_host_unregister(cj_ctx* c, void* p) {
+    if (!c || !p) return CJ_E_INVALID_ARG;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); cj_set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e)); return CJ_E_CUDA; }
     return CJ_OK;
 }
 int cj_memcpy_h2d(cj_ctx* c, void* d, const void* s, size_t bytes) {

@@ -99,8 +99,10 @@ struct cj_ctx {
     const unsigned* redo_ctr = nullptr;   // device counters of the most recent generation-4 launch ([1] = units handed to generation 2)
     bool redo_valid = false;
     std::mutex mu;
+    std::mutex mu_one;             // single device-resident unit calls (cj_*_ex with CJ_DEVICE)
     Scratch d_src, d_dst, d_desc, h_src, h_dst, h_desc;   // block-codec staging (run_host)
     Scratch f_dsrc, f_ddst, f_dtmp, f_ddesc, f_hsrc, f_hdst, f_hdesc;  // frame-container staging (frames.cu)
+    Scratch d_one;                                                     // descriptor words of a single device-resident unit (cj_*_ex)
     Scratch z_lit, z_enc;                                              // zstd per-warp literal buffers / encoder scratch (device)
     LzScratch g4;                                                      // thread-per-block LZ decode: counters + redo list (device)
     cj_ctx() {
@@ -108,7 +110,7 @@ struct cj_ctx {
         f_hsrc.pinned = f_hdst.pinned = f_hdesc.pinned = true;
     }
     void release_all() {
-        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc, &g4.fixed_};
+        Scratch* all[] = {&d_src, &d_dst, &d_desc, &h_src, &h_dst, &h_desc, &f_dsrc, &f_ddst, &f_dtmp, &f_ddesc, &f_hsrc, &f_hdst, &f_hdesc, &z_lit, &z_enc, &g4.fixed_, &d_one};
         for (Scratch* s : all) s->release();
     }
 };

@@ -71,8 +71,39 @@ public:
     size_t vlen = 0;
     size_t pos = 0;
 
+    // Pinned staging (north_star: "Buffer gains a pinned-host/device staging path", reference src/io.rs:370-375): with
+    // pinned=True the owned storage is kept page-locked (cj_host_register over the vector's capacity), so that codec calls
+    // between two pinned Buffers run as CJ_PINNED — the engine DMAs straight from / to these pages, no staging copy.
+    bool pinned = false;
+    uint8_t* reg_ptr = nullptr;   // start of the range that is registered right now
+
     Buffer() = default;
     explicit Buffer(Bytes&& v) : own(std::move(v)) {}
+    Buffer(const Buffer&) = delete;
+    ~Buffer() { unregister(); }
+
+    void unregister() {
+        if (reg_ptr) {
+            cj_host_unregister(engine(), reg_ptr);
+            reg_ptr = nullptr;
+        }
+    }
+    // call before anything that may reallocate the vector: registered pages must not be freed underneath the driver
+    void reserve(size_t n) {
+        if (n > own.capacity()) {
+            unregister();
+            own.reserve(std::max(n, own.capacity() + own.capacity() / 2));
+        }
+    }
+    // true when the storage is page-locked and may be handed to the engine as CJ_PINNED
+    bool dma_ready() {
+        if (!pinned || is_view() || own.capacity() == 0) return false;
+        if (reg_ptr != own.data()) {
+            unregister();
+            if (cj_host_register(engine(), own.data(), own.capacity()) == CJ_OK) reg_ptr = own.data();
+        }
+        return reg_ptr == own.data();
+    }
 
     bool is_view() const { return !view_ref.is_none() && view_ref.ptr() != nullptr; }
     uint8_t* data() { return is_view() ? vptr : own.data(); }
@@ -157,9 +188,27 @@ struct PyBuf {  // src/io.rs:177-335 PythonBuffer: PyObject_GetBuffer(PyBUF_CONT
     PyBuf(const PyBuf&) = delete;
 };
 
+// A device-resident array (anything exposing __cuda_array_interface__: torch / cupy / numba CUDA arrays).  Returns false
+// when `h` is not one; raises BufferError when it is but is not contiguous.
+static bool cuda_array(py::handle h, uint8_t** ptr, size_t* nbytes, bool* readonly) {
+    if (py::isinstance<Buffer>(h) || PyObject_CheckBuffer(h.ptr())) return false;
+    if (!PyObject_HasAttrString(h.ptr(), "__cuda_array_interface__")) return false;
+    py::dict d = h.attr("__cuda_array_interface__").cast<py::dict>();
+    if (d.contains("strides") && !d["strides"].is_none()) raise(PyExc_BufferError, "device array is not C contiguous");
+    py::tuple data = d["data"].cast<py::tuple>();
+    *ptr = reinterpret_cast<uint8_t*>(data[0].cast<uintptr_t>());
+    *readonly = data[1].cast<bool>();
+    const std::string ts = d["typestr"].cast<std::string>();
+    size_t n = (size_t)std::atoi(ts.c_str() + 2);
+    for (py::handle e : d["shape"].cast<py::tuple>()) n *= e.cast<size_t>();
+    *nbytes = n;
+    return true;
+}
+
 struct Input {
     const uint8_t* p = nullptr;
     size_t n = 0;
+    bool dma = false;   // host pages that are page-locked (a pinned Buffer)
     std::unique_ptr<PyBuf> pb;
     Bytes tmp;  // File contents (read from the current position to the end)
     explicit Input(py::handle h) {
@@ -168,6 +217,7 @@ struct Input {
             b.realign();
             p = b.data();  // whole buffer, cursor ignored (src/lib.rs:229-233, src/io.rs:389-392)
             n = b.size();
+            dma = b.dma_ready();
         } else if (py::isinstance<File>(h)) {
             tmp = h.cast<File&>().read_to_end();
             p = tmp.data();
@@ -192,7 +242,7 @@ static size_t deliver(py::handle out, const uint8_t* p, size_t n, PyObject* err_
             std::memcpy(b.vptr + b.pos, p, n);
         } else {
             const size_t old = b.own.size();
-            if (b.pos + n > old) b.own.resize(b.pos + n);
+            if (b.pos + n > old) { b.reserve(b.pos + n); b.own.resize(b.pos + n); }
             if (b.pos > old) std::memset(b.own.data() + old, 0, b.pos - old);  // a write past the end zero-fills the gap (Cursor<Vec<u8>>)
             if (n) std::memcpy(b.own.data() + b.pos, p, n);
         }
@@ -286,13 +336,74 @@ static py::object generic_decompress(cj_codec codec, py::handle data, const py::
     pad_to_hint(out, opt_size(output_len));
     return make_buffer(std::move(out));
 }
+// Both sides device-resident: the call runs as CJ_DEVICE, nothing crosses PCIe.  Mixed pairs are refused (the caller decides
+// where a copy happens).  Returns false when neither side is a device array.
+static bool device_into(cj_codec codec, bool compress, py::handle input, py::handle output, int level, int accel, size_t* written) {
+    uint8_t *sp = nullptr, *dp = nullptr;
+    size_t sn = 0, dn = 0;
+    bool sro = false, dro = false;
+    const bool sd = cuda_array(input, &sp, &sn, &sro), dd = cuda_array(output, &dp, &dn, &dro);
+    if (!sd && !dd) return false;
+    PyObject* err = compress ? g_compression_error : g_decompression_error;
+    if (sd != dd) raise(PyExc_ValueError, "device arrays and host buffers cannot be mixed in one call: pass both sides as device arrays (or copy one side first)");
+    if (dro) raise(PyExc_BufferError, "output device array is read-only");
+    cj_params prm{level, accel, 0};
+    int rc;
+    std::string msg;
+    {
+        py::gil_scoped_release rel;
+        rc = compress ? cj_compress_ex(engine(), codec, CJ_DEVICE, sp, sn, dp, dn, written, &prm) : cj_decompress_ex(engine(), codec, CJ_DEVICE, sp, sn, dp, dn, written);
+        if (rc) msg = cj_last_error();
+    }
+    if (rc) raise(err, msg);
+    return true;
+}
+
+// Output is an owned Buffer: the engine writes straight into its storage at the cursor (no intermediate vector), as
+// CJ_PINNED when both sides are page-locked.  `cap` = the most the call may produce.
+static size_t into_buffer(cj_codec codec, bool compress, const Input& in, Buffer& b, size_t cap, int level, int accel) {
+    const size_t old = b.own.size();
+    b.reserve(b.pos + cap);
+    if (b.pos + cap > old) b.own.resize(b.pos + cap);
+    if (b.pos > old) std::memset(b.own.data() + old, 0, b.pos - old);
+    const cj_mem where = (in.dma && b.dma_ready()) ? CJ_PINNED : CJ_HOST;
+    cj_params prm{level, accel, 0};
+    size_t written = 0;
+    int rc;
+    std::string msg;
+    {
+        py::gil_scoped_release rel;
+        rc = compress ? cj_compress_ex(engine(), codec, where, in.p, in.n, b.own.data() + b.pos, cap, &written, &prm)
+                      : cj_decompress_ex(engine(), codec, where, in.p, in.n, b.own.data() + b.pos, cap, &written);
+        if (rc) msg = cj_last_error();
+    }
+    if (rc) {
+        b.own.resize(old);
+        raise(compress ? g_compression_error : g_decompression_error, msg);
+    }
+    b.own.resize(std::max(old, b.pos + written));
+    b.pos += written;
+    return written;
+}
+
 static size_t generic_compress_into(cj_codec codec, py::handle input, py::handle output, int level) {
+    size_t dw = 0;
+    if (device_into(codec, true, input, output, level, 1, &dw)) return dw;
     Input in(input);
+    if (py::isinstance<Buffer>(output) && !output.cast<Buffer&>().is_view())
+        return into_buffer(codec, true, in, output.cast<Buffer&>(), cj_compress_bound(codec, in.n), level, 1);
     Bytes c = do_compress(codec, in.p, in.n, level);
     return deliver(output, c.data(), c.size(), g_compression_error);
 }
 static size_t generic_decompress_into(cj_codec codec, py::handle input, py::handle output) {
+    size_t dw = 0;
+    if (device_into(codec, false, input, output, -1, 1, &dw)) return dw;
     Input in(input);
+    if (py::isinstance<Buffer>(output) && !output.cast<Buffer&>().is_view()) {
+        size_t bound = 0;
+        if (cj_decompress_bound(codec, in.p, in.n, &bound)) raise(g_decompression_error, cj_last_error());
+        return into_buffer(codec, false, in, output.cast<Buffer&>(), bound, -1, 1);
+    }
     const size_t cap = output_capacity(output);
     size_t produced = 0;
     Bytes d;
@@ -303,6 +414,65 @@ static size_t generic_decompress_into(cj_codec codec, py::handle input, py::hand
         d = do_decompress(codec, in.p, in.n, cap, &produced);
     }
     return deliver(output, d.data(), produced, g_decompression_error);
+}
+
+// ---- batch entry points (not in the reference's Python surface; SURVEY.md 7 step 7 / north_star: "many independent buffers"):
+//      a list of independent buffers goes to the engine as ONE cj_*_batch call — thousands of units per launch instead of
+//      one launch per buffer — and comes back as a list of Buffers.  `caps[i]` = capacity of output i.
+static py::list run_batch_call(cj_codec codec, bool compress, std::vector<std::unique_ptr<Input>>& ins, const std::vector<size_t>& skip,
+                               const std::vector<size_t>& caps, int level, int accel) {
+    const size_t n = ins.size();
+    std::vector<Bytes> outs(n);
+    std::vector<uint64_t> so(n), sl(n), dof(n), dc(n), dl(n, 0);
+    std::vector<int32_t> st(n, 0);
+    static uint8_t dummy[16];
+    uintptr_t sbase = UINTPTR_MAX, dbase = UINTPTR_MAX;
+    for (size_t i = 0; i < n; i++) {
+        outs[i] = Bytes(std::max<size_t>(caps[i], 1));
+        const uintptr_t sp = (uintptr_t)(ins[i]->n > skip[i] ? ins[i]->p + skip[i] : dummy);
+        sbase = std::min(sbase, sp);
+        dbase = std::min(dbase, (uintptr_t)outs[i].data());
+    }
+    for (size_t i = 0; i < n; i++) {
+        const uintptr_t sp = (uintptr_t)(ins[i]->n > skip[i] ? ins[i]->p + skip[i] : dummy);
+        so[i] = sp - sbase;
+        sl[i] = ins[i]->n > skip[i] ? ins[i]->n - skip[i] : 0;
+        dof[i] = (uintptr_t)outs[i].data() - dbase;
+        dc[i] = caps[i];
+    }
+    cj_batch b;
+    b.n = n;
+    b.src_base = (const void*)sbase; b.src_off = so.data(); b.src_len = sl.data();
+    b.dst_base = (void*)dbase; b.dst_off = dof.data(); b.dst_cap = dc.data();
+    b.dst_len = dl.data(); b.status = st.data();
+    cj_params prm{level, accel, 0};
+    int rc = 0;
+    std::string msg;
+    if (n) {
+        py::gil_scoped_release rel;
+        rc = compress ? cj_compress_batch(engine(), codec, CJ_HOST, &b, &prm) : cj_decompress_batch(engine(), codec, CJ_HOST, &b);
+        if (rc) msg = cj_last_error();
+    }
+    PyObject* err = compress ? g_compression_error : g_decompression_error;
+    if (rc) raise(err, msg);
+    py::list result;
+    for (size_t i = 0; i < n; i++) {
+        if (st[i] != CJ_OK) raise(err, "unit " + std::to_string(i) + ": " + cj_status_string(st[i]));
+        outs[i].resize((size_t)dl[i]);
+        result.append(make_buffer(std::move(outs[i])));
+    }
+    return result;
+}
+
+static py::list generic_batch(cj_codec codec, bool compress, py::iterable inputs, int level) {
+    std::vector<std::unique_ptr<Input>> ins;
+    for (py::handle h : inputs) ins.emplace_back(new Input(h));
+    std::vector<size_t> skip(ins.size(), 0), caps(ins.size());
+    for (size_t i = 0; i < ins.size(); i++) {
+        if (compress) caps[i] = cj_compress_bound(codec, ins[i]->n);
+        else if (cj_decompress_bound(codec, ins[i]->p, ins[i]->n, &caps[i])) raise(g_decompression_error, "unit " + std::to_string(i) + ": " + cj_last_error());
+    }
+    return run_batch_call(codec, compress, ins, skip, caps, level, 1);
 }
 
 // ---- streaming classes (src/io.rs:760-814, src/lib.rs:299-395): host-side accumulation feeding the engine ----
@@ -444,8 +614,9 @@ PYBIND11_MODULE(cramjam, m) {
 
     // ------------------------------------------------------------------ Buffer
     py::class_<Buffer>(m, "Buffer", py::buffer_protocol())
-        .def(py::init([](py::object data, py::object copy) {
+        .def(py::init([](py::object data, py::object copy, bool pinned) {
                  auto* b = new Buffer();
+                 b->pinned = pinned;
                  if (data.is_none()) return b;
                  const bool do_copy = copy.is_none() ? true : copy.cast<bool>();
                  try {
@@ -472,7 +643,14 @@ PYBIND11_MODULE(cramjam, m) {
                  }
                  return b;
              }),
-             py::arg("data") = py::none(), py::arg("copy") = py::none())
+             py::arg("data") = py::none(), py::arg("copy") = py::none(), py::arg("pinned") = false)
+        .def_property_readonly("pinned", [](Buffer& b) { return b.pinned; },
+                               "True when the Buffer keeps its storage page-locked for direct DMA (not in the reference: the B200 staging path)")
+        .def("reserve", [](Buffer& b, size_t n) {
+            if (b.is_view()) raise(PyExc_OSError, "Cannot reserve on unowned buffer");
+            b.reserve(n);
+            return b.own.capacity();
+        }, py::arg("n"), "Grow the capacity to at least n bytes (a pinned Buffer registers its pages once for that capacity)")
         .def_buffer([](Buffer& b) {
             b.realign();
             return py::buffer_info(b.data(), 1, "B", 1, {(py::ssize_t)b.size()}, {(py::ssize_t)1}, /*readonly=*/true);
@@ -528,6 +706,7 @@ PYBIND11_MODULE(cramjam, m) {
         .def("tell", [](Buffer& b) { b.realign(); return b.pos; })
         .def("set_len", [](Buffer& b, size_t size) {
             if (b.is_view()) raise(PyExc_OSError, "Cannot set length on unowned buffer");
+            b.reserve(size);
             b.own.resize(size, 0);
         }, py::arg("size"))
         .def("truncate", [](Buffer& b) {
@@ -640,6 +819,8 @@ PYBIND11_MODULE(cramjam, m) {
         s.def("compress_raw", [](py::handle data, py::object) { return generic_compress(CJ_SNAPPY_RAW, data, -1); }, py::arg("data"), py::arg("output_len") = py::none());
         s.def("decompress_raw", [](py::handle data, py::object) { return generic_decompress(CJ_SNAPPY_RAW, data, py::none()); }, py::arg("data"), py::arg("output_len") = py::none());
         s.def("compress_raw_into", [](py::handle input, py::handle output) {
+            size_t dw = 0;
+            if (device_into(CJ_SNAPPY_RAW, true, input, output, -1, 1, &dw)) return dw;   // device arrays on both sides: CJ_DEVICE
             Input in(input);
             PyBuf out(output);  // as_bytes_mut(): slice semantics
             if ((size_t)out.b.len < cj_compress_bound(CJ_SNAPPY_RAW, in.n)) raise(g_compression_error, "snappy: output buffer (size = " + std::to_string(out.b.len) + ") is smaller than required (size = " + std::to_string(cj_compress_bound(CJ_SNAPPY_RAW, in.n)) + ")");
@@ -648,6 +829,8 @@ PYBIND11_MODULE(cramjam, m) {
             return c.size();
         }, py::arg("input"), py::arg("output"));
         s.def("decompress_raw_into", [](py::handle input, py::handle output) {
+            size_t dw = 0;
+            if (device_into(CJ_SNAPPY_RAW, false, input, output, -1, 1, &dw)) return dw;
             Input in(input);
             PyBuf out(output);
             size_t produced = 0;
@@ -655,6 +838,12 @@ PYBIND11_MODULE(cramjam, m) {
             if (produced) std::memcpy(out.b.buf, d.data(), produced);
             return produced;
         }, py::arg("input"), py::arg("output"));
+        s.def("decompress_raw_batch", [](py::iterable inputs) { return generic_batch(CJ_SNAPPY_RAW, false, inputs, -1); }, py::arg("inputs"),
+              "Decompress a list of independent raw snappy blocks in one engine call; returns a list of Buffers");
+        s.def("compress_raw_batch", [](py::iterable inputs) { return generic_batch(CJ_SNAPPY_RAW, true, inputs, -1); }, py::arg("inputs"),
+              "Compress a list of independent buffers into raw snappy blocks in one engine call; returns a list of Buffers");
+        s.def("decompress_batch", [](py::iterable inputs) { return generic_batch(CJ_SNAPPY_FRAMED, false, inputs, -1); }, py::arg("inputs"));
+        s.def("compress_batch", [](py::iterable inputs) { return generic_batch(CJ_SNAPPY_FRAMED, true, inputs, -1); }, py::arg("inputs"));
         s.def("compress_raw_max_len", [](py::handle data) { Input in(data); return cj_compress_bound(CJ_SNAPPY_RAW, in.n); }, py::arg("data"));
         s.def("decompress_raw_len", [](py::handle data) {
             Input in(data);
@@ -706,6 +895,10 @@ PYBIND11_MODULE(cramjam, m) {
             return make_buffer(std::move(buf));
         }, py::arg("data"), py::arg("output_len") = py::none());
         l.def("decompress_block_into", [](py::handle input, py::handle output, py::object output_len) {
+            {   // device arrays on both sides: a raw block (no size prefix: the output array's size is the capacity), CJ_DEVICE
+                size_t dw = 0;
+                if (device_into(CJ_LZ4_BLOCK, false, input, output, -1, 1, &dw)) return dw;
+            }
             Input in(input);
             const bool size_stored = output_len.is_none();
             PyBuf out(output);
@@ -725,6 +918,11 @@ PYBIND11_MODULE(cramjam, m) {
             return written;
         }, py::arg("input"), py::arg("output"), py::arg("output_len") = py::none());
         l.def("compress_block_into", [](py::handle data, py::handle output, py::object, py::object acceleration, py::object compression, py::object store_size) {
+            {   // device arrays on both sides: the raw block without a size prefix, CJ_DEVICE
+                size_t dw = 0;
+                if (device_into(CJ_LZ4_BLOCK, true, data, output, compression.is_none() ? -1 : compression.cast<int>(),
+                                acceleration.is_none() ? 1 : acceleration.cast<int>(), &dw)) return dw;
+            }
             Input in(data);
             PyBuf out(output);
             Bytes c = lz4_block_compress(in.p, in.n, store_size.is_none() ? true : store_size.cast<bool>(), acceleration.is_none() ? 1 : acceleration.cast<int>(),
@@ -734,6 +932,51 @@ PYBIND11_MODULE(cramjam, m) {
             return c.size();
         }, py::arg("data"), py::arg("output"), py::arg("mode") = py::none(), py::arg("acceleration") = py::none(), py::arg("compression") = py::none(),
               py::arg("store_size") = py::none());
+        l.def("decompress_block_batch", [](py::iterable inputs, py::object output_lens) {
+            // output_lens=None: every block carries the 4-byte size prefix compress_block(store_size=True) writes
+            std::vector<std::unique_ptr<Input>> ins;
+            for (py::handle h : inputs) ins.emplace_back(new Input(h));
+            std::vector<size_t> skip(ins.size(), 0), caps(ins.size());
+            if (output_lens.is_none()) {
+                for (size_t i = 0; i < ins.size(); i++) {
+                    if (ins[i]->n < 4) raise(g_decompression_error, "unit " + std::to_string(i) + ": Source buffer must at least contain size prefix.");
+                    int32_t v;
+                    std::memcpy(&v, ins[i]->p, 4);
+                    if (v < 0 || (uint32_t)v > 0x7E000000u) raise(g_decompression_error, "unit " + std::to_string(i) + ": bad size prefix");
+                    caps[i] = (size_t)v;
+                    skip[i] = 4;
+                }
+            } else {
+                size_t i = 0;
+                for (py::handle h : output_lens.cast<py::iterable>()) { if (i < caps.size()) caps[i] = h.cast<size_t>(); i++; }
+                if (i != caps.size()) raise(PyExc_ValueError, "output_lens must have one entry per input");
+            }
+            return run_batch_call(CJ_LZ4_BLOCK, false, ins, skip, caps, -1, 1);
+        }, py::arg("inputs"), py::arg("output_lens") = py::none(),
+              "Decompress a list of independent LZ4 blocks in one engine call; returns a list of Buffers");
+        l.def("compress_block_batch", [](py::iterable inputs, py::object acceleration, py::object compression, py::object store_size) {
+            const bool prefix = store_size.is_none() ? true : store_size.cast<bool>();
+            std::vector<std::unique_ptr<Input>> ins;
+            for (py::handle h : inputs) ins.emplace_back(new Input(h));
+            std::vector<size_t> skip(ins.size(), 0), caps(ins.size());
+            for (size_t i = 0; i < ins.size(); i++) caps[i] = cj_compress_bound(CJ_LZ4_BLOCK, ins[i]->n);
+            py::list raw = run_batch_call(CJ_LZ4_BLOCK, true, ins, skip, caps, compression.is_none() ? -1 : compression.cast<int>(),
+                                          acceleration.is_none() ? 1 : acceleration.cast<int>());
+            if (!prefix) return raw;
+            py::list out;
+            for (size_t i = 0; i < ins.size(); i++) {
+                Buffer& b = raw[i].cast<Buffer&>();
+                Bytes v(b.own.size() + 4);
+                const uint32_t ul = (uint32_t)ins[i]->n;
+                std::memcpy(v.data(), &ul, 4);
+                if (!b.own.empty()) std::memcpy(v.data() + 4, b.own.data(), b.own.size());
+                out.append(make_buffer(std::move(v)));
+            }
+            return out;
+        }, py::arg("inputs"), py::arg("acceleration") = py::none(), py::arg("compression") = py::none(), py::arg("store_size") = py::none());
+        l.def("decompress_batch", [](py::iterable inputs) { return generic_batch(CJ_LZ4_FRAME, false, inputs, -1); }, py::arg("inputs"));
+        l.def("compress_batch", [lvl](py::iterable inputs, py::object level) { return generic_batch(CJ_LZ4_FRAME, true, inputs, lvl(level)); }, py::arg("inputs"),
+              py::arg("level") = py::none());
         l.def("compress_block_bound", [](py::handle src) { Input in(src); return cj_compress_bound(CJ_LZ4_BLOCK, in.n) + 4; }, py::arg("src"));
         add_stream_classes<1>(l, CJ_LZ4_FRAME, 2, 4);
     }
@@ -749,6 +992,10 @@ PYBIND11_MODULE(cramjam, m) {
         z.def("compress_into", [lvl](py::handle input, py::handle output, py::object level) { return generic_compress_into(CJ_ZSTD, input, output, lvl(level)); },
               py::arg("input"), py::arg("output"), py::arg("level") = py::none());
         z.def("decompress_into", [](py::handle input, py::handle output) { return generic_decompress_into(CJ_ZSTD, input, output); }, py::arg("input"), py::arg("output"));
+        z.def("decompress_batch", [](py::iterable inputs) { return generic_batch(CJ_ZSTD, false, inputs, -1); }, py::arg("inputs"),
+              "Decompress a list of independent zstd streams in one engine call; returns a list of Buffers");
+        z.def("compress_batch", [lvl](py::iterable inputs, py::object level) { return generic_batch(CJ_ZSTD, true, inputs, lvl(level)); }, py::arg("inputs"),
+              py::arg("level") = py::none());
         add_stream_classes<2>(z, CJ_ZSTD, 1, 0);
     }
 }

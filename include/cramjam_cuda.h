@@ -140,6 +140,16 @@ int cj_decompress(cj_ctx* ctx, cj_codec codec, const void* src, size_t src_len, 
 int cj_compress(cj_ctx* ctx, cj_codec codec, const void* src, size_t src_len, void* dst, size_t dst_cap, size_t* written,
                 const cj_params* params);
 
+/* The same for a buffer pair that lives in pinned host memory (CJ_PINNED: payload DMA'd straight from / to the caller's
+ * pages, no staging copy) or in device memory (CJ_DEVICE: nothing is copied; the unit descriptors are staged by the
+ * engine).  This is what `Buffer`'s pinned / device staging path of the host binding calls (reference src/io.rs:370-375:
+ * RustyBuffer gains a pinned-host / device backing; north_star).  Frame codecs whose container walk needs host-visible
+ * bytes (snappy framing, LZ4 frame compress) reject CJ_DEVICE. */
+int cj_decompress_ex(cj_ctx* ctx, cj_codec codec, cj_mem where, const void* src, size_t src_len, void* dst, size_t dst_cap,
+                     size_t* written);
+int cj_compress_ex(cj_ctx* ctx, cj_codec codec, cj_mem where, const void* src, size_t src_len, void* dst, size_t dst_cap,
+                   size_t* written, const cj_params* params);
+
 /* ---- synthetic "Silesia-like" corpus: identical bytes from the host and the
  *      device generator for the same (seed, first_index); used by tests and bench.py ---------- */
 int cj_synth_blocks(cj_ctx* ctx, cj_mem where, void* dst, size_t n_blocks, size_t block_len, uint64_t seed,
@@ -156,6 +166,10 @@ int cj_device_alloc(cj_ctx* ctx, size_t bytes, void** out);
 int cj_device_free(cj_ctx* ctx, void* p);
 int cj_pinned_alloc(cj_ctx* ctx, size_t bytes, void** out);
 int cj_pinned_free(cj_ctx* ctx, void* p);
+/* Page-locks / releases an existing host range so that CJ_PINNED calls may DMA from / to it (the host binding's
+ * Buffer(pinned=True) keeps its storage registered). */
+int cj_host_register(cj_ctx* ctx, void* p, size_t bytes);
+int cj_host_unregister(cj_ctx* ctx, void* p);
 int cj_memcpy_h2d(cj_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on stream */
 int cj_memcpy_d2h(cj_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on stream */
 

@@ -255,3 +255,66 @@ def test_zstd_frames_are_valid_for_libzstd(cj):
         pytest.skip("no libzstd")
     for raw in (b"", b"abc", corpus.text(300000, 7)):
         assert S.zstd_decompress(bytes(cj.zstd.compress(raw)), len(raw)) == raw
+
+
+# ---- the B200 staging path of Buffer and the batch entry points (not in the reference's surface) ----
+def test_pinned_buffer_roundtrip(cj):
+    raw = corpus.text(3_000_000, 11)
+    src = cj.Buffer(raw, pinned=True)
+    assert src.pinned and len(src) == len(raw)
+    for variant in VARIANTS:
+        mod = getattr(cj, variant)
+        comp = cj.Buffer(pinned=True)
+        n = mod.compress_into(src, comp)
+        assert n == len(comp) and n < len(raw)
+        back = cj.Buffer(pinned=True)
+        back.reserve(len(raw))
+        m = mod.decompress_into(comp, back)
+        assert m == len(raw) and bytes(back) == raw
+        # the same Buffers again (storage stays registered), and appending at the cursor
+        m2 = mod.decompress_into(comp, back)
+        assert m2 == len(raw) and len(back) == 2 * len(raw) and bytes(back)[len(raw):] == raw
+        # a pinned output and a pageable input still work (staged path)
+        out2 = cj.Buffer(pinned=True)
+        assert mod.decompress_into(bytes(comp), out2) == len(raw) and bytes(out2) == raw
+
+
+def test_device_arrays_cuda_array_interface(cj):
+    import torch
+    raw = corpus.lz_model(60000, 5)
+    t_raw = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    for name, comp_into, decomp_into, bound in (
+            ("snappy raw", cj.snappy.compress_raw_into, cj.snappy.decompress_raw_into, cj.snappy.compress_raw_max_len(raw)),
+            ("lz4 block", lambda a, b: cj.lz4.compress_block_into(a, b, store_size=False), cj.lz4.decompress_block_into, cj.lz4.compress_block_bound(raw))):
+        t_comp = torch.zeros(bound, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        n = comp_into(t_raw, t_comp)
+        assert 0 < n < len(raw), name
+        t_back = torch.zeros(len(raw), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        m = decomp_into(t_comp[:n], t_back)
+        assert m == len(raw) and t_back.cpu().numpy().tobytes() == raw, name
+    # zstd frames decode device to device as well
+    zc = torch.frombuffer(bytearray(bytes(cj.zstd.compress(raw))), dtype=torch.uint8).cuda()
+    t_back = torch.zeros(len(raw), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    assert cj.zstd.decompress_into(zc, t_back) == len(raw) and t_back.cpu().numpy().tobytes() == raw
+    with pytest.raises(ValueError):
+        cj.snappy.decompress_raw_into(t_raw, bytearray(10))
+
+
+def test_batch_entry_points(cj):
+    datas = [corpus.text(n, n) for n in (10, 1000, 70000, 300000)] + [corpus.random_bytes(5000, 1), b"", corpus.lz_model(65536, 2)]
+    got = cj.snappy.decompress_raw_batch(cj.snappy.compress_raw_batch(datas))
+    assert [bytes(b) for b in got] == datas and all(isinstance(b, cj.Buffer) for b in got)
+    # units the engine made must equal what the single-buffer call makes (same kernels, same bytes)
+    assert [bytes(b) for b in cj.snappy.compress_raw_batch(datas)] == [bytes(cj.snappy.compress_raw(d)) for d in datas]
+    assert [bytes(b) for b in cj.lz4.decompress_block_batch(cj.lz4.compress_block_batch(datas))] == datas
+    nonempty = [d for d in datas if d]
+    blocks = cj.lz4.compress_block_batch(nonempty, store_size=False)
+    assert [bytes(b) for b in cj.lz4.decompress_block_batch(blocks, output_lens=[len(d) for d in nonempty])] == nonempty
+    for mod in (cj.snappy, cj.lz4, cj.zstd):
+        assert [bytes(b) for b in mod.decompress_batch(mod.compress_batch(datas))] == datas
+        assert [bytes(b) for b in mod.decompress_batch([mod.compress(d) for d in datas])] == datas
+    with pytest.raises(cj.DecompressionError):
+        cj.snappy.decompress_raw_batch([bytes(cj.snappy.compress_raw(b"abc")), b"sknow"])
