@@ -12,6 +12,8 @@
 // order); XXH32 header / block / content checksums are verified in the same kernel.  The encoders
 // emit independent 64 KiB blocks (legal LZ4F), one unit of the block encoder each.
 #include <chrono>
+#include <functional>
+#include <future>
 
 #include "internal.h"
 #include "lz_decode.cuh"
@@ -366,6 +368,38 @@ inline uint32_t h_rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return 
 inline void h_wr32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
 inline uint32_t h_xxh32(const uint8_t* p, size_t n) { return xxh32_generic([&](uint64_t q) { return p[q]; }, n, 0); }
 
+// XXH32's four accumulators are serial chains (acc = rotl(acc + w * P2, 13) * P1): one large frame cannot be hashed faster
+// than one chain step per 16 bytes, ~1.5 GB/s at GPU clocks (xxh32_warp below) against ~6 GB/s on one host core.  A frame
+// of at least HOST_HASH_MIN bytes whose bytes are on the host anyway (CJ_HOST / CJ_PINNED input of the encoder, output of
+// the decoder on its way home) is therefore hashed there, on a thread of its own next to the GPU work or the copy home —
+// a checksum of host-resident bytes, no codec step.  Device-resident frames (CJ_DEVICE) and small ones stay on the kernel.
+constexpr size_t HOST_HASH_MIN = (size_t)1 << 20;
+inline uint32_t h_xxh32_words(const uint8_t* p, size_t n) {
+    const uint8_t* const end = p + n;
+    uint32_t h;
+    if (n >= 16) {
+        uint32_t v1 = XP1 + XP2, v2 = XP2, v3 = 0, v4 = 0u - XP1;
+        const uint8_t* const lim = end - 16;
+        do {
+            uint32_t w[4];
+            memcpy(w, p, 16);
+            v1 = rotl32(v1 + w[0] * XP2, 13) * XP1;
+            v2 = rotl32(v2 + w[1] * XP2, 13) * XP1;
+            v3 = rotl32(v3 + w[2] * XP2, 13) * XP1;
+            v4 = rotl32(v4 + w[3] * XP2, 13) * XP1;
+            p += 16;
+        } while (p <= lim);
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+    } else {
+        h = XP5;
+    }
+    h += (uint32_t)n;
+    while (p + 4 <= end) { uint32_t w; memcpy(&w, p, 4); h = rotl32(h + w * XP3, 17) * XP4; p += 4; }
+    while (p < end) { h = rotl32(h + (uint32_t)*p * XP5, 11) * XP1; p++; }
+    h ^= h >> 15; h *= XP2; h ^= h >> 13; h *= XP3; h ^= h >> 16;
+    return h;
+}
+
 // Chunk / block size of the snappy-framed and LZ4-frame encoders.  Both formats allow chunks smaller than 64 KiB; one warp
 // needs ~4 ms to compress (1 ms to decompress) 64 KiB, so a small input is cut finer to put more warps on it:
 // 64 KiB from 4 MiB up, else n / 64 rounded up to 4 KiB, at least 16 KiB (1 MiB -> 64 chunks of 16 KiB).
@@ -443,7 +477,10 @@ int upload_units(cj_ctx* c, const cj_batch* bt, int where, std::vector<uint64_t>
 }
 
 // Copies produced bytes of every OK unit from the device destination arena back to the caller.
-int download_units(cj_ctx* c, const cj_batch* bt, int where, const std::vector<uint64_t>& dbase, size_t arena_bytes) {
+// `landed(unit_bytes)`, if given, runs on a thread of its own once the units' bytes are in host memory — next to the copy
+// from the pinned staging arena into the caller's pages (CJ_HOST) — with unit_bytes(i) = where unit i's bytes can be read.
+int download_units(cj_ctx* c, const cj_batch* bt, int where, const std::vector<uint64_t>& dbase, size_t arena_bytes,
+                   const std::function<void(const std::function<const uint8_t*(size_t)>&)>& landed = nullptr) {
     const size_t n = bt->n;
     uint8_t* hd = (uint8_t*)bt->dst_base;
     if (where == CJ_PINNED) {
@@ -451,12 +488,16 @@ int download_units(cj_ctx* c, const cj_batch* bt, int where, const std::vector<u
             if (bt->status[i] == CJ_OK && bt->dst_len[i])
                 CUDA_TRY(cudaMemcpyAsync(hd + bt->dst_off[i], (uint8_t*)c->f_ddst.p + dbase[i], (size_t)bt->dst_len[i], cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (landed) landed([&](size_t i) { return (const uint8_t*)hd + bt->dst_off[i]; });
     } else {
         int rc;
         if ((rc = c->f_hdst.ensure(arena_bytes + 64))) return rc;
         if (arena_bytes) CUDA_TRY(cudaMemcpyAsync(c->f_hdst.p, c->f_ddst.p, arena_bytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const uint8_t* stage = (const uint8_t*)c->f_hdst.p;
+        std::thread side;
+        if (landed) side = std::thread([&]() { landed([&](size_t i) { return stage + dbase[i]; }); });
+        struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join{side};
         if (n <= 4) {
             for (size_t i = 0; i < n; i++)
                 if (bt->status[i] == CJ_OK && bt->dst_len[i]) cj_parallel_copy(hd + bt->dst_off[i], stage + dbase[i], (size_t)bt->dst_len[i]);
@@ -753,6 +794,17 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
     std::vector<uint64_t> sbase;
     int rc;
     PhaseTrace tr(c, "lz4f_compress");
+    // content checksums of large inputs: on host threads, next to the upload and the block encoder (see HOST_HASH_MIN)
+    std::vector<std::future<uint32_t>> host_hash(n);
+    {
+        const uint8_t* hs = (const uint8_t*)bt->src_base;
+        for (size_t i = 0; i < n; i++)
+            if (bt->src_len[i] >= HOST_HASH_MIN) {
+                const uint8_t* p = hs + bt->src_off[i];
+                const size_t len = (size_t)bt->src_len[i];
+                host_hash[i] = std::async(std::launch::async, [p, len]() { return h_xxh32_words(p, len); });
+            }
+    }
     if ((rc = upload_units(c, bt, where, sbase))) return rc;
     tr.mark("upload");
     const size_t slot = cj_align16(65536 + 65536 / 255 + 16);
@@ -760,7 +812,7 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
     for (size_t i = 0; i < n; i++) {
         bt->status[i] = CJ_OK;
         bt->dst_len[i] = 0;
-        whole.add(sbase[i], bt->src_len[i], 0, 0);
+        whole.add(sbase[i], host_hash[i].valid() ? 0 : bt->src_len[i], 0, 0);
         const uint64_t piece = frame_piece(bt->src_len[i]);
         for (uint64_t p = 0; p < bt->src_len[i]; p += piece) ch.add(sbase[i] + p, std::min<uint64_t>(piece, bt->src_len[i] - p), ch.size() * slot, slot);
     }
@@ -831,7 +883,7 @@ int lz4f_compress(cj_ctx* c, int where, const cj_batch* bt, const cj_params* par
         }
         uint8_t tail[8];
         h_wr32(tail, 0);
-        h_wr32(tail + 4, content_xxh[i]);
+        h_wr32(tail + 4, host_hash[i].valid() ? host_hash[i].get() : content_xxh[i]);
         hdr.add(hb.size(), 8, dacc + pos, 0);
         hb.insert(hb.end(), tail, tail + 8);
         pos += 8;
@@ -999,6 +1051,8 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
                 else sum_of.push_back(~(size_t)0);
             }
     }
+    struct LateSum { size_t unit, off, len; uint32_t want; };
+    std::vector<LateSum> late;   // content checksums verified on the host while the output is copied home (HOST_HASH_MIN)
     std::vector<char> serial(n, 0);
     for (size_t i = 0; i < n; i++) serial[i] = !par[i];
     if (nblk) {
@@ -1027,12 +1081,13 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         // place every block; anything unusual sends the whole unit to the warp-per-frame kernel
         Items mv_dec, mv_raw, whole;      // temp slot -> final, stored payload -> final, frames to checksum
         std::vector<uint32_t> whole_want, whole_owner;
+        late.clear();
         size_t flat = 0;
         for (size_t i = 0; i < n; i++) {
             if (!par[i]) continue;
             uint64_t pos = 0;
             bool ok = true;
-            const size_t m0 = mv_dec.size(), r0 = mv_raw.size(), w0 = whole.size();
+            const size_t m0 = mv_dec.size(), r0 = mv_raw.size(), w0 = whole.size(), l0 = late.size();
             for (const Lz4fFrame& f : frames[i]) {
                 const uint64_t fstart = pos;
                 for (size_t k = f.first_block; k < f.first_block + f.n_blocks; k++, flat++) {
@@ -1054,7 +1109,10 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
                     pos += produced;
                 }
                 if (ok && f.has_csize && f.csize != pos - fstart) ok = false;
-                if (ok && f.has_csum) { whole.add(dbase[i] + fstart, pos - fstart, 0, 0); whole_want.push_back(f.want_csum); whole_owner.push_back((uint32_t)i); }
+                if (ok && f.has_csum) {
+                    if (where != CJ_DEVICE && pos - fstart >= HOST_HASH_MIN) late.push_back({i, (size_t)fstart, (size_t)(pos - fstart), f.want_csum});
+                    else { whole.add(dbase[i] + fstart, pos - fstart, 0, 0); whole_want.push_back(f.want_csum); whole_owner.push_back((uint32_t)i); }
+                }
             }
             if (!ok) {
                 serial[i] = 1;
@@ -1062,6 +1120,7 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
                 mv_raw.so.resize(r0); mv_raw.sl.resize(r0); mv_raw.dof.resize(r0); mv_raw.dc.resize(r0);
                 whole.so.resize(w0); whole.sl.resize(w0); whole.dof.resize(w0); whole.dc.resize(w0);
                 whole_want.resize(w0); whole_owner.resize(w0);
+                late.resize(l0);
             } else {
                 bt->dst_len[i] = pos;
             }
@@ -1104,7 +1163,16 @@ int lz4f_decompress(cj_ctx* c, int where, const cj_batch* bt) {
         for (size_t k = 0; k < ser.size(); k++) { bt->dst_len[ser_unit[k]] = st[k] == CJ_OK ? dl[k] : 0; bt->status[ser_unit[k]] = st[k]; }
     }
     tr.mark("serial units");
-    rc = download_units(c, bt, where, dbase, dacc);
+    std::vector<char> bad(n, 0);
+    std::function<void(const std::function<const uint8_t*(size_t)>&)> verify;
+    if (!late.empty())
+        verify = [&](const std::function<const uint8_t*(size_t)>& unit_bytes) {
+            for (const LateSum& L : late)
+                if (!serial[L.unit] && bt->status[L.unit] == CJ_OK && h_xxh32_words(unit_bytes(L.unit) + L.off, L.len) != L.want) bad[L.unit] = 1;
+        };
+    rc = download_units(c, bt, where, dbase, dacc, verify);
+    for (size_t i = 0; i < n; i++)
+        if (bad[i]) { bt->status[i] = CJ_ST_CHECKSUM; bt->dst_len[i] = 0; }
     tr.mark("download");
     return rc;
 }

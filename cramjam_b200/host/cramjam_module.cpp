@@ -920,6 +920,9 @@ PYBIND11_MODULE(cramjam, m) {
         l.def("compress_block_into", [](py::handle data, py::handle output, py::object, py::object acceleration, py::object compression, py::object store_size) {
             {   // device arrays on both sides: the raw block without a size prefix, CJ_DEVICE
                 size_t dw = 0;
+                if (PyObject_HasAttrString(data.ptr(), "__cuda_array_interface__") && !PyObject_CheckBuffer(data.ptr()) &&
+                    (store_size.is_none() || store_size.cast<bool>()))
+                    raise(PyExc_ValueError, "device arrays hold raw LZ4 blocks: pass store_size=False (the size prefix is a host-side convention)");
                 if (device_into(CJ_LZ4_BLOCK, true, data, output, compression.is_none() ? -1 : compression.cast<int>(),
                                 acceleration.is_none() ? 1 : acceleration.cast<int>(), &dw)) return dw;
             }

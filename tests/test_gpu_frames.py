@@ -160,3 +160,21 @@ def test_lz4f_large_frames_block_parallel_path_matches_oracle():
     assert st[0] == 0
     outs, st = ctx().run_host_units(capi.LZ4_FRAME, False, enc, [len(data)])
     assert st[0] == 0 and outs[0] == data
+
+
+@pytest.mark.parametrize("where", [capi.HOST, capi.PINNED])
+def test_lz4_frame_large_host_hashed_content_checksum(where):
+    """Frames of >= 1 MiB in host memory have their content checksum computed / verified on the host next to the GPU
+    work (frames.cu HOST_HASH_MIN): the frame must still be the format's, and a corrupted checksum must still fail."""
+    d = corpus.text(3_500_000, 9) + corpus.random_bytes(70_000, 1)
+    outs, st = ctx().run_host_units(capi.LZ4_FRAME, True, [d, d[:1_200_000], b"small"], [capi.lib().cj_compress_bound(capi.LZ4_FRAME, len(d))] * 3, where=where)
+    assert (st == 0).all()
+    for c, want in zip(outs, (d, d[:1_200_000], b"small")):
+        assert O.lz4f_decompress(c) == want                        # the oracle verifies header, block and content checksums
+    back, st = ctx().run_host_units(capi.LZ4_FRAME, False, outs, [len(d), 1_200_000, 5], where=where)
+    assert (st == 0).all() and back == [d, d[:1_200_000], b"small"]
+    bad = bytearray(outs[0]); bad[-2] ^= 0x40                      # content checksum of the large frame
+    _, st = ctx().run_host_units(capi.LZ4_FRAME, False, [bytes(bad), outs[1]], [len(d), 1_200_000], where=where)
+    assert st[0] == 7 and st[1] == 0
+    with pytest.raises(O.OracleError):
+        O.lz4f_decompress(bytes(bad))
