@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz4f_decode_kerne
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t* smem_warp = smem + (size_t)warp * DEC_SMEM_WARP;
+    ring_barrier_init(smem_warp, lane);
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
         if (u >= b.n) break;
@@ -1350,21 +1351,26 @@ int snappy_raw_compress_split(cj_ctx* c, int where, const cj_batch* bt) {
     int rc;
     if ((rc = upload_units(c, bt, where, sbase))) return rc;
     auto varint = [](uint64_t v, uint8_t* out) { int k = 0; do { uint8_t b = v & 0x7f; v >>= 7; if (v) b |= 0x80; out[k++] = b; } while (v); return k; };
-    const size_t slot = cj_align16(32 + 65536 + 65536 / 6);
     Items enc;
     std::vector<size_t> first(n + 1, 0);
+    size_t slot_acc = 0;
     for (size_t i = 0; i < n; i++) {
         first[i] = enc.size();
         const uint64_t L = bt->src_len[i];
+        // only units above 128 KiB are cut (the rule run_batch routes by): a smaller unit that shares a batch with a large
+        // one is compressed as one block, byte for byte what it is when it comes alone
+        const uint64_t piece = L > (128u << 10) ? 65536 : std::max<uint64_t>(L, 1);
         uint64_t p = 0;
         do {
-            const uint64_t len = std::min<uint64_t>(65536, L - p);
-            enc.add(sbase[i] + p, len, enc.size() * slot, slot);
+            const uint64_t len = std::min<uint64_t>(piece, L - p);
+            const size_t cap = cj_align16(32 + (size_t)len + (size_t)len / 6);
+            enc.add(sbase[i] + p, len, slot_acc, cap);
+            slot_acc += cap;
             p += len;
         } while (p < L);
     }
     first[n] = enc.size();
-    if ((rc = c->f_dtmp.ensure(enc.size() * slot + 64))) return rc;
+    if ((rc = c->f_dtmp.ensure(slot_acc + 64))) return rc;
     const size_t need = 2 * DescCarver::bytes_for(enc.size()) + DescCarver::bytes_for(n) + 192;
     if ((rc = c->f_ddesc.ensure(need))) return rc;
     if ((rc = c->f_hdesc.ensure(need))) return rc;

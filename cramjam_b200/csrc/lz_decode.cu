@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz_decode_kernel(
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t* smem_warp = smem + (size_t)warp * DEC_SMEM_WARP;
+    ring_barrier_init(smem_warp, lane);
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
         if (u >= b.n) break;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, CJ_DEC_CTAS) lz_decode_list_ke
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t* smem_warp = smem + (size_t)warp * DEC_SMEM_WARP;
+    ring_barrier_init(smem_warp, lane);
     const uint32_t count = ctr[1];
     for (;;) {
         const uint32_t i = next_unit(&ctr[2], lane);

@@ -77,6 +77,32 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
+// ---- bulk asynchronous copies (TMA; cp.async.bulk -> SASS UBLKCP) and the mbarrier that tracks the loads ----
+// The rings of the warp-per-block kernels are staged with them (north_star: "input/output staged through shared memory via
+// TMA bulk copies"): one elected lane hands a 16-byte aligned span to the copy engine, no lane moves a byte of it.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W;\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {   // global -> shared, completes on mbar
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {   // shared -> global, joins the thread's bulk group
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }   // the group's writes are performed
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // my shared-memory writes -> async proxy
+
 struct OutRing {
     static constexpr uint32_t CHUNK = ORING / 8;    // largest span moved between room checks (serial path)
     static constexpr uint32_t FLUSH_T = ORING / 4;  // drain when this many bytes are pending
@@ -91,6 +117,7 @@ struct OutRing {
     uint32_t op;       // bytes produced so far
     uint32_t flushed;  // bytes already stored to global
     uint32_t base;     // lowest output position a back-reference may reach (0; or the block start inside an independent-block frame)
+    uint32_t settled;  // output below this position is in global memory for certain; [settled, flushed) may still be on its way (bulk store in flight)
     int lane;
 
     __device__ __forceinline__ void init(uint8_t* ring_, uint8_t* dst_, int lane_) {
@@ -101,9 +128,20 @@ struct OutRing {
         op = 0;
         flushed = 0;
         base = 0;
+        settled = 0;
         lane = lane_;
     }
     __device__ __forceinline__ uint32_t ridx(uint32_t p) const { return ring + ((p + a) & OMASK); }  // shared address of output byte p
+
+    // Waits for the bulk store in flight: afterwards everything below `flushed` can be re-read from global memory (far
+    // back-references, frame checksums) and its ring bytes may be overwritten.
+    __device__ __forceinline__ void settle() {
+        if (settled != flushed) {
+            if (lane == 0) bulk_wait_all();
+            __syncwarp();
+            settled = flushed;
+        }
+    }
 
     // Stores [flushed, upto) to global: ragged head by bytes, 16-byte vector body, and (final only) the tail.
     __device__ __forceinline__ void flush_to(uint32_t upto, bool final) {
@@ -116,9 +154,20 @@ struct OutRing {
             q += head;
         }
         const uint32_t vend = q + ((upto - q) & ~15u);
-        for (uint32_t p = q + lane * 16; p < vend; p += 512) {
-            uint4 v = lds128(ridx(p));
-            *reinterpret_cast<uint4*>(dst + p) = v;
+        if (vend > q) {
+            // the 16-byte aligned body leaves through the copy engine: at most two spans (the ring wraps), issued by lane 0 once
+            // every lane's ring writes are visible to the async proxy and the previous store has completed
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_wait_all();
+                const uint32_t r0 = (q + a) & OMASK, bytes = vend - q;
+                const uint32_t first = min(bytes, (uint32_t)ORING - r0);
+                bulk_store(dst + q, ring + r0, first);
+                if (bytes > first) bulk_store(dst + q + first, ring, bytes - first);
+                bulk_commit();
+            }
+            settled = q;   // lane 0 waited: everything before this store is in global memory
         }
         q = vend;
         if (final) {
@@ -126,6 +175,7 @@ struct OutRing {
             q = upto;
         }
         flushed = q;
+        if (final) settle();
         __syncwarp();
     }
     __device__ __forceinline__ void make_room() {
@@ -186,6 +236,7 @@ struct OutRing {
                     for (uint32_t i = lane; i < c; i += 32) sts8(ridx(op + i), lds8(ridx(s + i % off)));
                 }
             } else {  // far: the source was drained to global long ago (off > ORING - CHUNK >= c)
+                if (s + c > settled) settle();
                 for (uint32_t i = lane; i < c; i += 32) sts8(ridx(op + i), __ldcg(dst + s + i));
             }
             op += c;
@@ -298,8 +349,11 @@ struct InRing {
     uint32_t n;
     uint32_t a;       // src misalignment; "g" coordinate = pos + a, ring index = g & IMASK
     uint32_t loaded;  // g coordinate up to which the ring has been filled (multiple of 512)
+    uint32_t mbar;    // shared address of this warp's mbarrier (bulk loads complete on it); its phase parity lives in the word behind it
+    uint32_t parity;
     int lane;
 
+    // ring_ = this warp's input ring; the warp's mbarrier sits behind the element queue (ring_barrier_init, once per kernel)
     __device__ __forceinline__ void init(uint8_t* ring_, const uint8_t* src_, uint32_t n_, int lane_) {
         ring = smem_addr(ring_);
         ring_g = ring_;
@@ -308,6 +362,8 @@ struct InRing {
         a = (uint32_t)((uintptr_t)src_ & 15u);
         loaded = 0;
         lane = lane_;
+        mbar = ring + IRING + QCAP * 4;
+        parity = lds32(mbar + 8);
     }
     __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return lds8(ring + ((pos + a) & IMASK)); }
 
@@ -321,9 +377,14 @@ struct InRing {
         if (loaded < end_g && loaded + 512 <= limit) {
             __syncwarp();
             const uint8_t* base = src - a;  // 16-byte aligned
+            uint32_t tx = 0;                // bytes handed to the copy engine in this call
             do {
                 const uint32_t g0 = loaded + lane * 16;
-                if (g0 >= a && g0 + 16 <= a + n) {
+                if (loaded >= a && loaded + 512 <= a + n) {
+                    // a 512-byte row that lies wholly inside the input: one bulk copy (global -> ring), no lane touches it
+                    if (lane == 0) bulk_load(ring + (loaded & IMASK), base + loaded, 512u, mbar);
+                    tx += 512;
+                } else if (g0 >= a && g0 + 16 <= a + n) {
                     uint4 v = __ldg(reinterpret_cast<const uint4*>(base + g0));
                     sts128(ring + (g0 & IMASK), v);
                 } else if (g0 + 16 > a && g0 < a + n) {
@@ -334,10 +395,19 @@ struct InRing {
                 }
                 loaded += 512;
             } while (loaded < end_g && loaded + 512 <= limit);
+            if (tx) {   // (warp-uniform) wait for the rows: the parser reads them right away
+                if (lane == 0) mbar_arrive_expect_tx(mbar, tx);
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+                if (lane == 0) sts32(mbar + 8, parity);
+            }
             __syncwarp();
         }
     }
 };
+
+// Once per kernel and warp: the mbarrier of the warp's input ring (one arrival per refill: lane 0's expect_tx) and its parity word.
+__device__ __forceinline__ void ring_barrier_init(uint8_t* smem_warp, int lane);
 
 // Compressed size of the element that starts at p if it can go through the lane-parallel path,
 // else 0 (needs the serial path: unusual encoding, near the end of the block, or past it).
@@ -465,6 +535,7 @@ __device__ __forceinline__ uint32_t exec_lanes(OutRing& out, uint32_t cnt, uint3
     const bool smallM = ML != 0 && ML <= 16 && off >= ML && mdi + ML <= (uint32_t)ORING && (far || msi + ML <= (uint32_t)ORING);
     const uint8_t* msrc = far ? out.dst + (m - off) : out.ring_g + msi;                          // lane-parallel match source
     bool pending = ML != 0;
+    if (__any_sync(FULL, ML != 0 && far && se > out.settled)) out.settle();   // a far source inside the bulk store still in flight (rare)
 
     // ---- pass 1: literals (always ready); with EARLY_COPIES also every copy of a literal-free lane whose source precedes the batch ----
     {
@@ -645,6 +716,15 @@ __device__ int32_t decode_block(const uint8_t* __restrict__ src, uint32_t n, uin
 }
 
 constexpr int DEC_WARPS = 4;
-constexpr int DEC_SMEM_WARP = ORING + IRING + QCAP * 4;
+constexpr int DEC_SMEM_WARP = ORING + IRING + QCAP * 4 + 16;   // output ring | input ring | element queue | mbarrier + parity word
+
+__device__ __forceinline__ void ring_barrier_init(uint8_t* smem_warp, int lane) {
+    const uint32_t mbar = smem_addr(smem_warp + ORING + IRING + QCAP * 4);
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        sts32(mbar + 8, 0);
+    }
+    __syncwarp();
+}
 
 }  // namespace cj
