@@ -216,7 +216,7 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
         else if (codec == CJ_ZSTD) {
             int rc = c->z_enc.ensure(cj::zstd_enc_scratch_bytes(c->sm_count, b.n));
             if (rc) return rc;
-            e = cj::launch_zstd_encode(b, counters, (uint8_t*)c->z_enc.p, c->sm_count, c->stream);
+            e = cj::launch_zstd_encode(b, counters, (uint8_t*)c->z_enc.p, c->sm_count, params ? params->level : 0, c->stream);
         }
         else { cj_set_error("codec %d has no device-resident batch encoder", codec); return CJ_E_INVALID_ARG; }
     }

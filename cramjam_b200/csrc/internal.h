@@ -31,7 +31,7 @@ cudaError_t launch_lz_encode(int codec, const Batch& b, unsigned* counter, int s
 cudaError_t launch_lz4f_decode(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream);
 cudaError_t launch_zstd_decode(const Batch& b, unsigned* counter, uint8_t* lit_scratch, int sm_count, cudaStream_t stream);
 size_t zstd_scratch_bytes(int sm_count, uint32_t n);
-cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, cudaStream_t stream);
+cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, int level, cudaStream_t stream);
 size_t zstd_enc_scratch_bytes(int sm_count, uint32_t n);
 cudaError_t launch_copy_units(uint32_t n, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* len, uint8_t* dst_base,
                               const uint64_t* dst_off, int sm_count, cudaStream_t stream);

@@ -5,19 +5,25 @@
 // real encoder so the API produces compressed frames rather than stored ones: LZ77 parsing by the same
 // warp-parallel greedy hash match finder as the LZ4 / Snappy encoders (lz_match.cuh), sequences coded
 // with FSE over the PREDEFINED literal-length / offset / match-length distributions (RFC 8878 3.1.1.3.2.2),
-// literals stored raw (no Huffman stage yet).  Ratio is therefore LZ4-class, not libzstd-level-3-class;
-// the `level` argument selects nothing.  Frames are single-segment with the pledged content size
+// literals Huffman-coded per block (zstd_huf.cuh: histogram by the warp, code lengths + tree description by one lane,
+// the four streams by four lanes) when that shrinks them, raw otherwise.  `level`: 1-2 (and negative levels) skip the
+// Huffman stage (fastest), everything else — the reference default 0 -> 3 included — runs it.  The match finder is the
+// greedy single-probe one of the block encoders, so the ratio stays below libzstd's at the same level.
+// Frames are single-segment with the pledged content size
 // (reference src/zstd.rs:45,61), blocks of <= 128 KiB; a block that does not shrink is emitted as a Raw_Block.
 // One warp per frame; the FSE state chain is serial per block and runs warp-uniformly.
 #include "internal.h"
 #include "lz_match.cuh"
+#include "zstd_huf.cuh"
 
 namespace cj {
 
 constexpr int ZE_WARPS = 4;
 constexpr uint32_t ZE_BLOCK = 128 * 1024;
 constexpr uint32_t ZE_MAXSEQ = ZE_BLOCK / 4 + 8;                       // every match is >= 4 bytes
-constexpr size_t ZE_SCRATCH = (size_t)ZE_MAXSEQ * 12 + ZE_BLOCK + 64;  // per warp: sequences (ll, ml, off) + literal bytes
+constexpr size_t ZE_HUF_TMP = 256 + 4 * ((size_t)ZE_BLOCK / 4 * 3 / 2 + 64);          // tree description + four streams at their worst case (11 bits per symbol)
+constexpr size_t ZE_SCRATCH = (size_t)ZE_MAXSEQ * 12 + ZE_BLOCK + 64 + ZE_HUF_TMP + 64;  // per warp: sequences (ll, ml, off) + literal bytes + Huffman scratch
+constexpr int ZE_HUF_SMEM = 256 * 4 + 256 * 2;   // per warp: literal histogram + code table (value | nbits << 12)
 
 struct ZEncTables {  // FSE compression tables of the predefined distributions + length->code maps
     uint16_t ll_state[64], of_state[32], ml_state[64];
@@ -83,8 +89,69 @@ struct ZSeqEmitter {
 
 // Encodes one block src[b0, b1) into out (room for at least (b1-b0) + 16 bytes).  Returns the block content size
 // written at out, or 0 if the block should be stored raw.
+// Huffman-coded literals section (Compressed_Literals_Block) of `nlit` literal bytes at out; returns its size or 0 when the
+// literals should be stored raw instead (too few, alphabet beyond the direct tree description, or no gain).
+__device__ uint32_t ze_huf_literals(const uint8_t* lits, uint32_t nlit, uint8_t* tmp, uint32_t* hist, uint16_t* code, uint8_t* out, int lane) {
+    if (nlit < 256) return 0;
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&hist[lits[i]], 1u);
+    __syncwarp();
+    // ---- code lengths, canonical codes and the tree description: one lane (serial by nature, ~100 symbols) ----
+    uint32_t tree_len = 0, est = 0;
+    if (lane == 0) {
+        uint8_t nbits[256];
+        const int mb = zh::build_lengths(hist, nbits);
+        if (mb) {
+            tree_len = (uint32_t)zh::write_tree_direct(nbits, mb, tmp);   // parked at the start of the scratch, copied below
+            if (tree_len) {
+                zh::assign_codes(nbits, mb, code);
+                uint64_t bits = 0;
+                for (int sym = 0; sym < 256; sym++) bits += (uint64_t)hist[sym] * nbits[sym];
+                est = (uint32_t)(bits / 8) + 4 + 6 + tree_len;
+            }
+        }
+    }
+    tree_len = __shfl_sync(FULL, tree_len, 0);
+    est = __shfl_sync(FULL, est, 0);
+    if (!tree_len || est + (nlit >> 6) + 8 >= nlit) return 0;
+    __syncwarp();
+    // ---- the streams: four lanes, one stream each (a stream is a serial bit chain), into the scratch behind the tree ----
+    const bool four = nlit >= 1024;
+    const uint32_t seg = four ? (nlit + 3) / 4 : nlit;
+    const uint32_t slot = seg + seg / 2 + 64;   // a stream's worst case: 11 bits per symbol (ZE_HUF_TMP holds four of them)
+    uint8_t* streams = tmp + 256;
+    uint32_t sz = 0;
+    if (lane < (four ? 4 : 1)) {
+        const uint32_t a = lane * seg, b = (four && lane < 3) ? a + seg : nlit;
+        sz = zh::encode_stream(lits + a, b - a, code, streams + (size_t)lane * slot);
+    }
+    __syncwarp();
+    const uint32_t s0 = __shfl_sync(FULL, sz, 0), s1 = __shfl_sync(FULL, sz, 1), s2 = __shfl_sync(FULL, sz, 2), s3 = __shfl_sync(FULL, sz, 3);
+    const uint32_t comp = tree_len + (four ? 6 + s0 + s1 + s2 + s3 : s0);
+    if ((nlit < 1024 && comp >= 1024) || (nlit < 16384 && comp >= 16384) || comp + 8 >= nlit || (four && (s0 | s1 | s2) > 0xFFFFu)) return 0;
+    const uint32_t hl = (uint32_t)zh::header_len(nlit);
+    if (lane == 0) {
+        zh::write_header(out, nlit, comp, four);
+        if (four) {
+            uint8_t* j = out + hl + tree_len;
+            j[0] = (uint8_t)s0; j[1] = (uint8_t)(s0 >> 8); j[2] = (uint8_t)s1; j[3] = (uint8_t)(s1 >> 8); j[4] = (uint8_t)s2; j[5] = (uint8_t)(s2 >> 8);
+        }
+    }
+    for (uint32_t i = lane; i < tree_len; i += 32) out[hl + i] = tmp[i];
+    uint32_t op = hl + tree_len + (four ? 6 : 0);
+    const uint32_t sizes[4] = {s0, s1, s2, s3};
+    for (int k = 0; k < (four ? 4 : 1); k++) {
+        const uint8_t* sp = streams + (size_t)k * slot;
+        for (uint32_t i = lane; i < sizes[k]; i += 32) out[op + i] = sp[i];
+        op += sizes[k];
+    }
+    __syncwarp();
+    return op;
+}
+
 __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint32_t b1, enc_slot_t* table, uint32_t* seq, uint8_t* lits, uint8_t* out,
-                             int lane) {
+                             uint32_t* hist, uint16_t* code, bool huffman, int lane) {
     const uint32_t bsz = b1 - b0;
     uint32_t nseq = 0, nlit = 0;
     uint32_t anchor = b0;
@@ -99,14 +166,17 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
     for (uint32_t i = lane; i < tail; i += 32) lits[nlit + i] = __ldg(src + anchor + i);
     nlit += tail;
     __syncwarp();
-    // ---- literals section: Raw_Literals_Block ----
-    uint32_t op = 0;
-    if (nlit < 32) { if (lane == 0) out[0] = (uint8_t)(nlit << 3); op = 1; }
-    else if (nlit < 4096) { if (lane == 0) { out[0] = (uint8_t)((nlit << 4) | (1 << 2)); out[1] = (uint8_t)(nlit >> 4); } op = 2; }
-    else { if (lane == 0) { out[0] = (uint8_t)((nlit << 4) | (3 << 2)); out[1] = (uint8_t)(nlit >> 4); out[2] = (uint8_t)(nlit >> 12); } op = 3; }
-    if (op + nlit + 16 > bsz) return 0;
-    for (uint32_t i = lane; i < nlit; i += 32) out[op + i] = lits[i];
-    op += nlit;
+    // ---- literals section: Compressed_Literals_Block (Huffman) when it pays, else Raw_Literals_Block ----
+    uint32_t op = huffman ? ze_huf_literals(lits, nlit, lits + ZE_BLOCK + 64, hist, code, out, lane) : 0;
+    if (op == 0) {
+        if (nlit < 32) { if (lane == 0) out[0] = (uint8_t)(nlit << 3); op = 1; }
+        else if (nlit < 4096) { if (lane == 0) { out[0] = (uint8_t)((nlit << 4) | (1 << 2)); out[1] = (uint8_t)(nlit >> 4); } op = 2; }
+        else { if (lane == 0) { out[0] = (uint8_t)((nlit << 4) | (3 << 2)); out[1] = (uint8_t)(nlit >> 4); out[2] = (uint8_t)(nlit >> 12); } op = 3; }
+        if (op + nlit + 16 > bsz) return 0;
+        for (uint32_t i = lane; i < nlit; i += 32) out[op + i] = lits[i];
+        op += nlit;
+    }
+    if (op + 16 > bsz) return 0;
     // ---- sequences section: count, modes (all predefined), FSE bitstream written from the last sequence to the first ----
     if (nseq < 128) { if (lane == 0) out[op] = (uint8_t)nseq; op += 1; }
     else if (nseq < 0x7F00) { if (lane == 0) { out[op] = (uint8_t)((nseq >> 8) + 128); out[op + 1] = (uint8_t)nseq; } op += 2; }
@@ -153,8 +223,8 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
     return op + 3 < bsz ? op : 0;
 }
 
-__device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, enc_slot_t* table, uint8_t* scratch, int lane,
-                            uint32_t* produced) {
+__device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, enc_slot_t* table, uint8_t* scratch, uint32_t* hist,
+                            uint16_t* code, bool huffman, int lane, uint32_t* produced) {
     *produced = 0;
     const uint64_t bound = (uint64_t)n + 3ull * (n / ZE_BLOCK + 1) + 18;
     if (cap < bound) return CJ_ST_DST_SMALL;
@@ -177,7 +247,7 @@ __device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t
         const uint32_t b1 = min(n, b0 + ZE_BLOCK);
         const bool last = b1 >= n;
         const uint32_t bsz = b1 - b0;
-        uint32_t csz = bsz >= 64 ? ze_block(src, b0, b1, table, seq, lits, dst + op + 3, lane) : 0;
+        uint32_t csz = bsz >= 64 ? ze_block(src, b0, b1, table, seq, lits, dst + op + 3, hist, code, huffman, lane) : 0;
         __syncwarp();
         uint32_t bh;
         if (csz) {
@@ -196,11 +266,13 @@ __device__ int32_t ze_frame(const uint8_t* __restrict__ src, uint32_t n, uint8_t
     return CJ_OK;
 }
 
-__global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(Batch b, unsigned* __restrict__ counter, uint8_t* __restrict__ scratch) {
+__global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(Batch b, unsigned* __restrict__ counter, uint8_t* __restrict__ scratch, int huffman) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     enc_slot_t* table = reinterpret_cast<enc_slot_t*>(smem) + (size_t)warp * ENC_HSIZE;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + ENC_TABLE_BYTES * ZE_WARPS + (size_t)warp * ZE_HUF_SMEM);
+    uint16_t* code = reinterpret_cast<uint16_t*>(hist + 256);
     uint8_t* my_scratch = scratch + ((size_t)blockIdx.x * ZE_WARPS + warp) * ZE_SCRATCH;
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
@@ -209,7 +281,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32) zstd_encode_kernel(Batch b, uns
         uint32_t produced = 0;
         int32_t st;
         if (slen > MAX_UNIT) st = CJ_ST_TOO_BIG;
-        else st = ze_frame(b.src_base + b.src_off[u], (uint32_t)slen, b.dst_base + b.dst_off[u], b.dst_cap[u], table, my_scratch, lane, &produced);
+        else st = ze_frame(b.src_base + b.src_off[u], (uint32_t)slen, b.dst_base + b.dst_off[u], b.dst_cap[u], table, my_scratch, hist, code, huffman != 0, lane, &produced);
         __syncwarp();
         if (lane == 0) {
             b.dst_len[u] = st == CJ_OK ? produced : 0;
@@ -279,7 +351,7 @@ static cudaError_t upload_tables() {
 }
 
 int zstd_enc_grid(int sm_count, uint32_t n) {
-    int grid = sm_count * 6;  // 8 KiB of shared memory per warp (lz_match.cuh) and <= 80 registers: 24 warps per SM
+    int grid = sm_count * 5;  // 9.5 KiB of shared memory per warp (match table + Huffman histogram / codes): 20 warps per SM
     const int need = (int)((n + ZE_WARPS - 1) / ZE_WARPS);
     if (grid > need) grid = need;
     return grid < 1 ? 1 : grid;
@@ -287,8 +359,11 @@ int zstd_enc_grid(int sm_count, uint32_t n) {
 
 size_t zstd_enc_scratch_bytes(int sm_count, uint32_t n) { return (size_t)zstd_enc_grid(sm_count, n) * ZE_WARPS * ZE_SCRATCH; }
 
-cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, cudaStream_t stream) {
-    const size_t smem = ENC_TABLE_BYTES * ZE_WARPS;
+cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scratch, int sm_count, int level, cudaStream_t stream) {
+    const size_t smem = (ENC_TABLE_BYTES + ZE_HUF_SMEM) * ZE_WARPS;
+    // libzstd's levels trade speed for ratio; here: levels 1-2 and the negative ("fast") levels store literals raw, every
+    // other level (0 = the library default 3 included) adds the Huffman literal stage
+    const int huffman = (level == 1 || level == 2 || level < 0) ? 0 : 1;
     static bool ready = false;
     if (!ready) {
         cudaError_t e = upload_tables();
@@ -299,7 +374,7 @@ cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scrat
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
-    zstd_encode_kernel<<<zstd_enc_grid(sm_count, b.n), ZE_WARPS * 32, smem, stream>>>(b, counter, scratch);
+    zstd_encode_kernel<<<zstd_enc_grid(sm_count, b.n), ZE_WARPS * 32, smem, stream>>>(b, counter, scratch, huffman);
     return cudaGetLastError();
 }
 
