@@ -253,6 +253,7 @@ static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, c
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ENC_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
         ctas_per_sm = occ < 1 ? 1 : occ;
+        if (const char* v = getenv("CJ_ENC_CTAS")) { const int f = atoi(v); if (f >= 1 && f <= occ) ctas_per_sm = f; }   // experiments: resident CTAs per SM
     }
     int grid = sm_count * ctas_per_sm;  // persistent: every resident CTA slot, units handed out by the atomic queue
     const int need = (int)((b.n + ENC_WARPS - 1) / ENC_WARPS);
