@@ -38,15 +38,73 @@ __device__ __forceinline__ void match_table_reset(enc_slot_t* table, int lane) {
     __syncwarp();
 }
 
+// One 32-position window in flight between the two halves of a step (registers only).
+struct MatchWindow {
+    uint32_t v, v4, v8;        // this lane's position-side words at +0, +4, +8
+    uint32_t w0, w1, w2, w3;   // candidate-side words (aligned loads), shifted by `sh` when compared
+    uint32_t sh;               // candidate misalignment in bits
+    uint32_t cand, d;          // candidate position and distance
+    bool probe, deep;          // a candidate exists; all 12 bytes on both sides are inside the input
+};
+
+// First half of a step: hash the 32 positions of the window at p, look them up, insert them (highest position of a bucket
+// wins, whatever the store order), and START the loads of the candidate words.  Nothing here waits for global memory.
+template <int HBITS>
+__device__ __forceinline__ void match_probe(const uint8_t* __restrict__ src, uint32_t p, uint32_t start_limit, uint32_t v, uint32_t vn,
+                                            enc_slot_t* table, int lane, MatchWindow& w) {
+    const uint32_t pos = p + lane;
+    const bool valid = pos < start_limit;
+    const uint32_t h = (v * 0x9E3779B1u) >> (32 - HBITS);
+    uint32_t slot = 0;
+    if (valid) slot = table[h];
+    __syncwarp();
+    const uint32_t grp = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
+    if (valid && lane == 31 - __clz(grp)) table[h] = (enc_slot_t)pos;
+    __syncwarp();
+    w.d = (pos - slot) & 0xFFFFu;
+    w.cand = pos - w.d;
+    w.probe = valid && w.d != 0 && w.d <= pos;
+    // position-side words at +4 and +8 (real only while pos + 8 < start_limit)
+    const uint32_t v4a = __shfl_sync(FULL, v, (lane + 4) & 31), v4b = __shfl_sync(FULL, vn, (lane + 4) & 31);
+    const uint32_t v8a = __shfl_sync(FULL, v, (lane + 8) & 31), v8b = __shfl_sync(FULL, vn, (lane + 8) & 31);
+    w.v = v;
+    w.v4 = lane + 4 < 32 ? v4a : v4b;
+    w.v8 = lane + 8 < 32 ? v8a : v8b;
+    w.deep = pos + 8 < start_limit;
+    w.w0 = w.w1 = w.w2 = w.w3 = 0;
+    w.sh = 0;
+    if (w.probe) {
+        const uint32_t a = (uint32_t)((uintptr_t)(src + w.cand) & 3u);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(src + w.cand - a);
+        w.sh = a * 8;
+        w.w0 = __ldg(q);
+        w.w1 = __ldg(q + 1);   // holds cand + 3 or lies inside [cand, pos): always in bounds
+        if (w.deep) { w.w2 = __ldg(q + 2); w.w3 = __ldg(q + 3); }
+    }
+}
+
+// Second half: this lane's match length at its position: 0 none, 4..11 final, 12 = at least 12 (or not extended, see deep).
+__device__ __forceinline__ uint32_t match_verify(const MatchWindow& w) {
+    if (!w.probe) return 0;
+    const uint32_t c0 = __funnelshift_r(w.w0, w.w1, w.sh);
+    if (c0 != w.v) return 0;
+    if (!w.deep) return 4;
+    const uint32_t x1 = __funnelshift_r(w.w1, w.w2, w.sh) ^ w.v4, x2 = __funnelshift_r(w.w2, w.w3, w.sh) ^ w.v8;
+    return x1 ? 4 + ((__ffs(x1) - 1) >> 3) : (x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12);
+}
+
 // Scans src[begin, end): positions in [begin, start_limit) may start a match, a match may not pass
 // match_limit (start_limit <= match_limit - 3).  Returns the position where the trailing literal run starts.
 //
-// Per step of 32 positions the warp pays ONE dependent round trip to L1/L2: the 4-byte words of the next 32
-// positions are prefetched while the current ones are processed, and every lane that finds a verified
-// candidate extends its own match to 12 bytes right away (the words on the position side come from the
-// neighbouring lanes' registers by shuffle).  84 % of the matches of the bench corpus are <= 12 bytes and
-// need nothing more; longer ones are extended by the whole warp, 32 bytes per ballot.  The matches of a step
-// are chosen greedily in position order (registers only), then handed to the emitter together:
+// The scan advances one 32-position window per step and is software-pipelined over two windows: the table lookups and
+// candidate loads of window p + 32 (match_probe) are issued BEFORE the matches of window p are verified, chosen and emitted,
+// so the L2 / DRAM round trip of the candidate words — what a warp of the unpipelined scan sat waiting for most of its
+// time (ncu: 4.9 long-scoreboard stalls per issue, throughput linear in resident warps) — overlaps a whole step of work.
+// Every lane that finds a verified candidate has its match up to 12 bytes from registers (the position-side words come
+// from the neighbouring lanes by shuffle); 84 % of the bench corpus' matches need nothing more, longer ones are extended by
+// the whole warp, 32 bytes per ballot.  A match that reaches into later windows masks the lanes it covers there (they are
+// still inserted into the table); a match that covers whole windows makes the scan jump ahead.  The matches of a step are
+// chosen greedily in position order (registers only), then handed to the emitter together:
 //   em.window(src, p, v, anchor, sel, mlen, off)  all matches of the step at once, lane i of `sel` holding match
 //                                              (p + i, mlen, off); v = the lane's 4-byte word (its low byte is
 //                                              src[p + lane]); anchor = start of the pending literal run.
@@ -58,40 +116,23 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
                                                  enc_slot_t* table, int lane, Emitter& em) {
     uint32_t anchor = begin;
     uint32_t p = begin;
-    uint32_t v = p + lane < start_limit ? load32u(src + p + lane) : 0u;
-    while (p < start_limit) {
-        const uint32_t pos = p + lane;
-        const bool valid = pos < start_limit;
-        const uint32_t vn = pos + 32 < start_limit ? load32u(src + pos + 32) : 0u;  // next window, in flight during this step
-        const uint32_t h = (v * 0x9E3779B1u) >> (32 - HBITS);
-        uint32_t slot = 0;
-        if (valid) slot = table[h];
-        __syncwarp();
-        const uint32_t grp = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-        if (valid && lane == 31 - __clz(grp)) table[h] = (enc_slot_t)pos;  // highest position of the bucket wins
-        __syncwarp();
-        const uint32_t d = (pos - slot) & 0xFFFFu;
-        const uint32_t cand = pos - d;
-        const bool probe = valid && d != 0 && d <= pos;
-        // position-side words at +4 and +8 (real only while pos + 8 < start_limit)
-        const uint32_t v4a = __shfl_sync(FULL, v, (lane + 4) & 31), v4b = __shfl_sync(FULL, vn, (lane + 4) & 31);
-        const uint32_t v8a = __shfl_sync(FULL, v, (lane + 8) & 31), v8b = __shfl_sync(FULL, vn, (lane + 8) & 31);
-        const uint32_t v4 = lane + 4 < 32 ? v4a : v4b, v8 = lane + 8 < 32 ? v8a : v8b;
-        uint32_t mlen = 0;  // this lane's match length: 0 none, 4..11 final, 12 = at least 12 (or not extended: see deep)
-        const bool deep = pos + 8 < start_limit;  // all 12 bytes on both sides are inside the input
-        if (probe) {
-            const uint32_t a = (uint32_t)((uintptr_t)(src + cand) & 3u);
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(src + cand - a);
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);  // w1 holds cand + 3 or lies inside [cand, pos): always in bounds
-            const uint32_t c0 = __funnelshift_r(w0, w1, a * 8);
-            if (deep) {
-                const uint32_t w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-                const uint32_t x1 = __funnelshift_r(w1, w2, a * 8) ^ v4, x2 = __funnelshift_r(w2, w3, a * 8) ^ v8;
-                if (c0 == v) mlen = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : (x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12);
-            } else if (c0 == v) {
-                mlen = 4;
-            }
+    if (p >= start_limit) return anchor;
+    auto words = [&](uint32_t at) { return at + lane < start_limit ? load32u(src + at + lane) : 0u; };
+    uint32_t v1 = words(p + 32);
+    MatchWindow cur, nxt;
+    match_probe<HBITS>(src, p, start_limit, words(p), v1, table, lane, cur);
+    for (;;) {
+        // ---- first half of the NEXT window: its loads fly while this window is finished ----
+        const uint32_t p1 = p + 32;
+        const bool more = p1 < start_limit;
+        uint32_t v2 = 0;
+        if (more) {
+            v2 = words(p1 + 32);
+            match_probe<HBITS>(src, p1, start_limit, v1, v2, table, lane, nxt);
         }
+        // ---- second half of THIS window ----
+        uint32_t mlen = match_verify(cur);
+        const bool deep = cur.deep;
         uint32_t mm = __ballot_sync(FULL, mlen != 0);
         if (anchor > p) mm &= anchor - p >= 32 ? 0u : ~((1u << (anchor - p)) - 1);  // lanes covered by the previous match
         if (mm) {
@@ -103,7 +144,7 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
                 const uint32_t mpos = p + i;
                 uint32_t len = __shfl_sync(FULL, mlen, i);
                 if ((open_ended >> i) & 1) {  // extend the match, 32 bytes per ballot
-                    const uint32_t c = __shfl_sync(FULL, cand, i);
+                    const uint32_t c = __shfl_sync(FULL, cur.cand, i);
                     const uint32_t maxlen = match_limit - mpos;
                     for (;;) {
                         const uint32_t k = len + lane;
@@ -119,22 +160,31 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
                 const uint32_t covered = last_end - p;  // lanes below this were swallowed by the match
                 mm = covered >= 32 ? 0u : mm & ~((1u << covered) - 1);
             }
-            if (!em.window(src, p, v, anchor, sel, mlen, d)) {
+            if (!em.window(src, p, cur.v, anchor, sel, mlen, cur.d)) {
                 uint32_t s = sel, a = anchor;
                 while (s) {
                     const int i = __ffs(s) - 1;
                     s &= s - 1;
-                    const uint32_t len = __shfl_sync(FULL, mlen, i), off = __shfl_sync(FULL, d, i);
+                    const uint32_t len = __shfl_sync(FULL, mlen, i), off = __shfl_sync(FULL, cur.d, i);
                     em.serial(a, p + i - a, off, len);
                     a = p + i + len;
                 }
             }
             anchor = last_end;
         }
-        const uint32_t pnext = max(p + 32, anchor);
-        if (pnext == p + 32) v = vn;
-        else v = pnext + lane < start_limit ? load32u(src + pnext + lane) : 0u;
-        p = pnext;
+        if (!more) break;
+        if (anchor >= p1 + 32) {
+            // the last match covers the next window entirely (long runs): jump to the window that holds its end; the
+            // pipeline restarts there (the windows in between are not inserted into the table)
+            p = p1 + ((anchor - p1) & ~31u);
+            if (p >= start_limit) break;
+            v1 = words(p + 32);
+            match_probe<HBITS>(src, p, start_limit, words(p), v1, table, lane, cur);
+            continue;
+        }
+        cur = nxt;
+        v1 = v2;
+        p = p1;
     }
     return anchor;
 }
