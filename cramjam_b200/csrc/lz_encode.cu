@@ -179,7 +179,7 @@ struct BlockEmitter {
     }
 };
 
-template <int CODEC, int HBITS>
+template <int CODEC, int HBITS, int WAYS>
 __device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, uint64_t cap, enc_slot_t* table, int lane, uint32_t* produced) {
     *produced = 0;
     const uint64_t bound = CODEC == CJ_SNAPPY_RAW ? 32ull + n + n / 6 : (uint64_t)n + n / 255 + 16;
@@ -208,9 +208,9 @@ __device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uin
     const uint32_t match_limit = CODEC == CJ_SNAPPY_RAW ? n : (n >= 5 ? n - 5 : 0);
     uint32_t anchor = 0;
     if (start_limit > 0) {
-        match_table_reset<HBITS>(table, lane);
+        match_table_reset<HBITS + WAYS - 1>(table, lane);
         BlockEmitter<CODEC> em{o, src};
-        anchor = find_matches<BlockEmitter<CODEC>, HBITS>(src, 0, start_limit, match_limit, table, lane, em);
+        anchor = find_matches<BlockEmitter<CODEC>, HBITS, WAYS>(src, 0, start_limit, match_limit, table, lane, em);
     }
     if (CODEC == CJ_SNAPPY_RAW) snappy_emit_literal(o, src + anchor, n - anchor);
     else lz4_emit_sequence(o, src + anchor, n - anchor, 0, 0);
@@ -218,12 +218,12 @@ __device__ int32_t encode_block(const uint8_t* __restrict__ src, uint32_t n, uin
     return CJ_OK;
 }
 
-template <int CODEC, int HBITS>
+template <int CODEC, int HBITS, int WAYS>
 __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsigned* __restrict__ counter) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    enc_slot_t* table = reinterpret_cast<enc_slot_t*>(smem) + ((size_t)warp << HBITS);
+    enc_slot_t* table = reinterpret_cast<enc_slot_t*>(smem) + (((size_t)warp * WAYS) << HBITS);
     for (;;) {
         const uint32_t u = next_unit(counter, lane);
         if (u >= b.n) break;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsi
         uint32_t produced = 0;
         int32_t st;
         if (slen > MAX_UNIT) st = CJ_ST_TOO_BIG;
-        else st = encode_block<CODEC, HBITS>(b.src_base + b.src_off[u], (uint32_t)slen, b.dst_base + b.dst_off[u], b.dst_cap[u], table, lane, &produced);
+        else st = encode_block<CODEC, HBITS, WAYS>(b.src_base + b.src_off[u], (uint32_t)slen, b.dst_base + b.dst_off[u], b.dst_cap[u], table, lane, &produced);
         __syncwarp();
         if (lane == 0) {
             b.dst_len[u] = st == CJ_OK ? produced : 0;
@@ -240,10 +240,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) lz_encode_kernel(Batch b, unsi
     }
 }
 
-template <int CODEC, int HBITS>
+template <int CODEC, int HBITS, int WAYS = 1>
 static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, cudaStream_t stream, bool reset_counter) {
-    const size_t smem = (sizeof(enc_slot_t) << HBITS) * ENC_WARPS;
-    auto k = lz_encode_kernel<CODEC, HBITS>;
+    const size_t smem = (sizeof(enc_slot_t) << HBITS) * WAYS * ENC_WARPS;
+    auto k = lz_encode_kernel<CODEC, HBITS, WAYS>;
     static cj_per_device_flag ctas_flag;
     int& ctas_per_sm = ctas_flag.here();
     if (!ctas_per_sm) {
@@ -267,8 +267,9 @@ static cudaError_t launch_enc(const Batch& b, unsigned* counter, int sm_count, c
     return cudaGetLastError();
 }
 
-// effort: 0..3 = hash table of 2^10 .. 2^13 slots per warp (2 .. 16 KiB of shared memory).  A smaller table leaves room for
-// more resident warps and is faster; a larger one finds more matches.  Measured on the bench corpus (Snappy, 16 384 x 64 KiB):
+// effort: 0..2 = hash table of 2^10 .. 2^12 slots per warp (2 .. 8 KiB of shared memory); a smaller table leaves room for more
+// resident warps and is faster, a larger one finds more matches.  3 = the HC-class search: 2^12 buckets of two positions each
+// (a hash chain of depth two, 16 KiB), both candidates verified, and a lazy choice between neighbouring positions.  Measured on the bench corpus (Snappy, 16 384 x 64 KiB):
 // 2^10 92 GB/s ratio 1.64 | 2^11 85 GB/s 1.79 | 2^12 58 GB/s 1.92 (default).  lz4 `acceleration` (src/lz4.rs:113-131) lowers
 // the effort, HC-class levels (`compression=Some(n)`, lz4 frame level >= 3; src/lz4.rs:17,42-59) raise it.
 template <int CODEC>
@@ -276,7 +277,7 @@ static cudaError_t launch_enc_effort(int effort, const Batch& b, unsigned* count
     switch (effort) {
     case 0: return launch_enc<CODEC, 10>(b, counter, sm_count, stream, reset_counter);
     case 1: return launch_enc<CODEC, 11>(b, counter, sm_count, stream, reset_counter);
-    case 3: return launch_enc<CODEC, 13>(b, counter, sm_count, stream, reset_counter);
+    case 3: return launch_enc<CODEC, 12, 2>(b, counter, sm_count, stream, reset_counter);   // HC class: two candidates per position + lazy choice
     default: return launch_enc<CODEC, 12>(b, counter, sm_count, stream, reset_counter);
     }
 }

@@ -45,21 +45,32 @@ struct MatchWindow {
     uint32_t sh;               // candidate misalignment in bits
     uint32_t cand, d;          // candidate position and distance
     bool probe, deep;          // a candidate exists; all 12 bytes on both sides are inside the input
+    // second way of the bucket (WAYS == 2, the HC-class search): the position the bucket held before the most recent one
+    uint32_t x0, x1, x2, x3, xsh, cand2, d2;
+    bool probe2;
 };
 
 // First half of a step: hash the 32 positions of the window at p, look them up, insert them (highest position of a bucket
 // wins, whatever the store order), and START the loads of the candidate words.  Nothing here waits for global memory.
-template <int HBITS>
+// WAYS = 2: a bucket keeps its two most recent positions (a hash chain of depth two); both candidates are verified and the
+// longer match wins.  The bucket count is 2^HBITS either way, so the table is WAYS x 2^HBITS slots.
+template <int HBITS, int WAYS = 1>
 __device__ __forceinline__ void match_probe(const uint8_t* __restrict__ src, uint32_t p, uint32_t start_limit, uint32_t v, uint32_t vn,
                                             enc_slot_t* table, int lane, MatchWindow& w) {
     const uint32_t pos = p + lane;
     const bool valid = pos < start_limit;
     const uint32_t h = (v * 0x9E3779B1u) >> (32 - HBITS);
-    uint32_t slot = 0;
-    if (valid) slot = table[h];
+    uint32_t slot = 0, slot2 = 0;
+    if (valid) {
+        slot = table[WAYS * h];
+        if (WAYS == 2) slot2 = table[2 * h + 1];
+    }
     __syncwarp();
     const uint32_t grp = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-    if (valid && lane == 31 - __clz(grp)) table[h] = (enc_slot_t)pos;
+    if (valid && lane == 31 - __clz(grp)) {   // highest position of the bucket wins; with two ways the old head moves down
+        table[WAYS * h] = (enc_slot_t)pos;
+        if (WAYS == 2) table[2 * h + 1] = (enc_slot_t)slot;
+    }
     __syncwarp();
     w.d = (pos - slot) & 0xFFFFu;
     w.cand = pos - w.d;
@@ -81,16 +92,42 @@ __device__ __forceinline__ void match_probe(const uint8_t* __restrict__ src, uin
         w.w1 = __ldg(q + 1);   // holds cand + 3 or lies inside [cand, pos): always in bounds
         if (w.deep) { w.w2 = __ldg(q + 2); w.w3 = __ldg(q + 3); }
     }
+    w.probe2 = false;
+    if (WAYS == 2) {
+        w.d2 = (pos - slot2) & 0xFFFFu;
+        w.cand2 = pos - w.d2;
+        w.probe2 = valid && w.d2 != 0 && w.d2 <= pos && w.d2 != w.d;
+        w.x0 = w.x1 = w.x2 = w.x3 = 0;
+        w.xsh = 0;
+        if (w.probe2) {
+            const uint32_t a = (uint32_t)((uintptr_t)(src + w.cand2) & 3u);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(src + w.cand2 - a);
+            w.xsh = a * 8;
+            w.x0 = __ldg(q);
+            w.x1 = __ldg(q + 1);
+            if (w.deep) { w.x2 = __ldg(q + 2); w.x3 = __ldg(q + 3); }
+        }
+    }
 }
 
 // Second half: this lane's match length at its position: 0 none, 4..11 final, 12 = at least 12 (or not extended, see deep).
-__device__ __forceinline__ uint32_t match_verify(const MatchWindow& w) {
-    if (!w.probe) return 0;
-    const uint32_t c0 = __funnelshift_r(w.w0, w.w1, w.sh);
-    if (c0 != w.v) return 0;
-    if (!w.deep) return 4;
-    const uint32_t x1 = __funnelshift_r(w.w1, w.w2, w.sh) ^ w.v4, x2 = __funnelshift_r(w.w2, w.w3, w.sh) ^ w.v8;
+__device__ __forceinline__ uint32_t match_len12(bool probe, bool deep, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t sh, uint32_t v,
+                                                uint32_t v4, uint32_t v8) {
+    if (!probe) return 0;
+    const uint32_t c0 = __funnelshift_r(a0, a1, sh);
+    if (c0 != v) return 0;
+    if (!deep) return 4;
+    const uint32_t x1 = __funnelshift_r(a1, a2, sh) ^ v4, x2 = __funnelshift_r(a2, a3, sh) ^ v8;
     return x1 ? 4 + ((__ffs(x1) - 1) >> 3) : (x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12);
+}
+// With two ways the longer of the two candidates' matches is kept (the nearer one on a tie): cand / d are switched to it.
+template <int WAYS>
+__device__ __forceinline__ uint32_t match_verify(MatchWindow& w) {
+    const uint32_t m1 = match_len12(w.probe, w.deep, w.w0, w.w1, w.w2, w.w3, w.sh, w.v, w.v4, w.v8);
+    if (WAYS == 1) return m1;
+    const uint32_t m2 = match_len12(w.probe2, w.deep, w.x0, w.x1, w.x2, w.x3, w.xsh, w.v, w.v4, w.v8);
+    if (m2 > m1) { w.cand = w.cand2; w.d = w.d2; return m2; }
+    return m1;
 }
 
 // Scans src[begin, end): positions in [begin, start_limit) may start a match, a match may not pass
@@ -111,7 +148,9 @@ __device__ __forceinline__ uint32_t match_verify(const MatchWindow& w) {
 //                                              Returns false if it wants the step one match at a time instead:
 //   em.serial(anchor, literal_len, offset, match_len)  warp-uniform.
 // HBITS = log2 of the table size: the speed / ratio knob of the block encoders (lz4 `acceleration`, HC-class levels).
-template <class Emitter, int HBITS = ENC_HBITS>
+// WAYS = 2 adds the second candidate per position and a one-step lazy choice (a match is passed over when the next position
+// starts a longer one): the HC-class search of the block encoders (lz4 `compression=Some(n)`, lz4 frame level >= 3).
+template <class Emitter, int HBITS = ENC_HBITS, int WAYS = 1>
 __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src, uint32_t begin, uint32_t start_limit, uint32_t match_limit,
                                                  enc_slot_t* table, int lane, Emitter& em) {
     uint32_t anchor = begin;
@@ -120,7 +159,7 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
     auto words = [&](uint32_t at) { return at + lane < start_limit ? load32u(src + at + lane) : 0u; };
     uint32_t v1 = words(p + 32);
     MatchWindow cur, nxt;
-    match_probe<HBITS>(src, p, start_limit, words(p), v1, table, lane, cur);
+    match_probe<HBITS, WAYS>(src, p, start_limit, words(p), v1, table, lane, cur);
     for (;;) {
         // ---- first half of the NEXT window: its loads fly while this window is finished ----
         const uint32_t p1 = p + 32;
@@ -128,10 +167,10 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
         uint32_t v2 = 0;
         if (more) {
             v2 = words(p1 + 32);
-            match_probe<HBITS>(src, p1, start_limit, v1, v2, table, lane, nxt);
+            match_probe<HBITS, WAYS>(src, p1, start_limit, v1, v2, table, lane, nxt);
         }
         // ---- second half of THIS window ----
-        uint32_t mlen = match_verify(cur);
+        uint32_t mlen = match_verify<WAYS>(cur);
         const bool deep = cur.deep;
         uint32_t mm = __ballot_sync(FULL, mlen != 0);
         if (anchor > p) mm &= anchor - p >= 32 ? 0u : ~((1u << (anchor - p)) - 1);  // lanes covered by the previous match
@@ -143,6 +182,10 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
                 const int i = __ffs(mm) - 1;
                 const uint32_t mpos = p + i;
                 uint32_t len = __shfl_sync(FULL, mlen, i);
+                if (WAYS == 2 && i < 31 && ((mm >> (i + 1)) & 1)) {   // lazy: the next position starts a longer match -> one more literal
+                    const uint32_t len1 = __shfl_sync(FULL, mlen, i + 1);
+                    if (len < 12 && len1 > len) { mm &= mm - 1; continue; }
+                }
                 if ((open_ended >> i) & 1) {  // extend the match, 32 bytes per ballot
                     const uint32_t c = __shfl_sync(FULL, cur.cand, i);
                     const uint32_t maxlen = match_limit - mpos;
@@ -179,7 +222,7 @@ __device__ __forceinline__ uint32_t find_matches(const uint8_t* __restrict__ src
             p = p1 + ((anchor - p1) & ~31u);
             if (p >= start_limit) break;
             v1 = words(p + 32);
-            match_probe<HBITS>(src, p, start_limit, words(p), v1, table, lane, cur);
+            match_probe<HBITS, WAYS>(src, p, start_limit, words(p), v1, table, lane, cur);
             continue;
         }
         cur = nxt;
