@@ -52,6 +52,23 @@ __device__ __forceinline__ void g4_redo(const G4& g, uint32_t u) {
 }
 
 // predicated forms (no branch around them)
+//
+// Ordering of the far fetch.  A far back-reference is read with cp.async.ca (LDGSTS, L1-allocating) from the lane's OWN
+// output, which the same lane wrote earlier with plain st.global.v4.  What is relied on, and why it holds:
+//   (1) the bytes were stored by an instruction that precedes the fetch in program order by at least one whole
+//       sub-iteration (static_assert below: a far source lies entirely below the stored frontier), and no other thread
+//       ever writes or reads this block's output while the kernel runs;
+//   (2) the store and the fetch are issued by one warp through one LSU queue in program order; both are `asm volatile`
+//       with a "memory" clobber, so neither the compiler nor ptxas moves one across the other;
+//   (3) the L1 is write-through and a store that hits a resident line updates (or evicts) it — the same property that
+//       makes an ordinary ld.global after st.global by the same thread return the stored value — and LDGSTS performs the
+//       same L1 lookup as LDG; a fetch that misses goes to L2 behind the store on the same path.
+// The PTX memory model words the guarantee for ld/st; for the asynchronous copy we rely on (2) and (3) as properties of the
+// sm_100 memory pipeline.  Evidence: every decode test compares against the oracle bit for bit (including 131 072 blocks
+// per launch, tests/test_gpu_lz_decode4.py::test_multi_round_batch_configs4_size), bench.py verifies 4 GiB per run, and
+// compute-sanitizer memcheck / racecheck report nothing (profiles/r01_sanitizers.md).  (cp.async.cg — L2 only, no L1 line
+// that could go stale — exists for 16-byte copies only and would give up the L1 hits on the re-reads of a back-reference's
+// sector, which are what this kernel's speed hangs on)
 __device__ __forceinline__ void g4_cp_async8_if(uint32_t saddr, const void* gptr, uint32_t pred) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(saddr), "l"(gptr), "r"(pred) : "memory");
 }
