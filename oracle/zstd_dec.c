@@ -6,7 +6,7 @@
  * -> libcramjam::zstd::decompress -> zstd::stream::read::Decoder -> libzstd 1.5.7
  * (zstd-sys 2.0.14+zstd.1.5.7, un-vendored, Cargo.lock:1025-1050).  The streaming decoder
  * consumes every concatenated frame and skips skippable frames; so does this one.
- * Pinned in tests/test_oracle_zstd.py against tests/golden/plaintext.txt.zst and against
+ * Pinned in tests/test_oracle_goldens.py / tests/test_oracle_cross.py against tests/golden/plaintext.txt.zst and against
  * frames produced by the system libzstd.so.1 at levels 1..19 over many shapes of input.
  */
 #include "cj_oracle.h"
