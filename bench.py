@@ -521,7 +521,8 @@ def run_ours(args):
             ctx.set_decode_path(2, 1)
             ms_g = timed(step_device, k=3)
             assert int((t_st != 0).sum()) == 0
-            codecs["snappy_block_decompress_warp_per_block"] = record(ms_g, B, U, float(clen.sum()), "lz_decode_kernel<snappy, lane-parallel>", streams="as the headline")
+            codecs["snappy_block_decompress_warp_per_block"] = record(ms_g, B, U, float(clen.sum()), "lz_decode_kernel<snappy, lane-parallel> (rings staged by cp.async.bulk)",
+                                                                      streams="as the headline", traffic=ncu_traffic("snappy_block_decompress_warp_per_block", B))
         except Exception as e:
             codecs["gen2_error"] = repr(e)[:200]
         finally:
