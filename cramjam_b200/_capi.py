@@ -148,8 +148,9 @@ class Context:
         _check(lib().cj_ctx_synchronize(self._h))
 
     def set_decode_path(self, generation, min_units=32768):
-        """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 3 = index walk + lane
-        state machines, 4 = one thread per block (Snappy; the default), 5 = 4 and 2 side by side on a split Snappy batch."""
+        """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 4 = one thread per
+        block with 8-byte chunks (lz_decode4.cu), 7 = one thread per block with 16-byte chunks and linear per-lane records
+        (lz_decode7.cu)."""
         _check(lib().cj_ctx_set_decode_path(self._h, generation, min_units))
 
     def last_redo_count(self):

@@ -79,6 +79,8 @@ struct LzScratch {
 namespace cj {
 // One thread per block (lz_decode4.cu, Snappy raw and LZ4 block) + the generation-2 kernel over whatever it declines.
 cudaError_t launch_lz_decode4(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream);
+// The same, generation 7 (lz_decode7.cu): 16-byte chunks, linear per-lane records.
+cudaError_t launch_lz_decode7(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream);
 }
 
 struct cj_ctx {

@@ -1,5 +1,5 @@
-"""-m gpu parity tests of the thread-per-block decode path (generation 4, lz_decode4.cu: Snappy raw and LZ4 block) with
-its generation-2 redo list, forced on through cj_ctx_set_decode_path() for every batch size, and of batches beyond one
+"""-m gpu parity tests of the thread-per-block decode paths (generation 4, lz_decode4.cu, and generation 7, lz_decode7.cu:
+Snappy raw and LZ4 block) with their generation-2 redo list, each forced on through cj_ctx_set_decode_path() for every batch size, and of batches beyond one
 wave of the kernel (the multi-round path).  Same oracle, same status-code expectations as test_gpu_lz_decode.py."""
 import numpy as np
 import pytest
@@ -16,10 +16,10 @@ pytestmark = pytest.mark.gpu
 CASES = corpus.edge_cases()
 
 
-@pytest.fixture(autouse=True)
-def gen4():
+@pytest.fixture(autouse=True, params=[4, 7], ids=["gen4", "gen7"])
+def gen4(request):
     default = ctx().decode_path()
-    ctx().set_decode_path(4, 1)
+    ctx().set_decode_path(request.param, 1)
     yield
     ctx().set_decode_path(*default)
 
@@ -41,7 +41,7 @@ def test_synthetic_blocks_bit_exact(codec):
     dst, do, dl, st = gpu_decode_device(codec, src, so, sl, [U] * n)
     assert (st == 0).all() and (dl == U).all()
     assert np.array_equal(dst[:n * U], data)
-    if ctx().decode_path()[0] == 4:   # well-formed, aligned blocks are decoded by the thread-per-block kernel itself, not by its fallback
+    if ctx().decode_path()[0] in (4, 7):   # well-formed, aligned blocks are decoded by the thread-per-block kernel itself, not by its fallback
         assert ctx().last_redo_count() == 0
 
 
