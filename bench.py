@@ -382,7 +382,8 @@ def run_ours(args):
     clocks = sampler.stop(wall0, wall1) if sampler else None
     total_blocks = B * world
     gen, min_units = ctx.decode_path()
-    kernel_name = "g4_kernel<snappy> (one thread per block) + lz_decode_list_kernel (redo list)" if (gen == 4 and B >= min_units) else "lz_decode_kernel<snappy, lane-parallel> (one warp per block)"
+    tpb = f"g{gen}_kernel" if (gen in (4, 7) and B >= min_units) else None   # the thread-per-block kernel that decodes batches of this size
+    kernel_name = f"{tpb}<snappy> (one thread per block) + lz_decode_list_kernel (redo list)" if tpb else "lz_decode_kernel<snappy, lane-parallel> (one warp per block)"
     value = total_blocks * U / (ms_dev * 1e6)
     alg_bytes = float(clen.sum()) + float(B) * U   # per launch on this rank: compressed read + uncompressed written
     achieved = alg_bytes / (ms_dev * 1e6)
@@ -474,7 +475,7 @@ def run_ours(args):
             barrier()
             ms_m = max_over_ranks(timed(step_mixed, k=3, warm=1))
             cbytes = sum(p[6] for p in parts.values())
-            extras["mixed_snappy_lz4_configs4"] = record(ms_m, MB, U, cbytes, "g4_kernel<snappy> then g4_kernel<lz4>, one batched call per codec",
+            extras["mixed_snappy_lz4_configs4"] = record(ms_m, MB, U, cbytes, f"{tpb or 'lz_decode_kernel'}<snappy> then {tpb or 'lz_decode_kernel'}<lz4>, one batched call per codec",
                                                          whole_job_GBps=MB * world * U / (ms_m * 1e6), blocks_per_gpu=MB, n_gpus=world,
                                                          streams="GPU encoders; even global block index = snappy, odd = lz4; generated per rank from the global index")
             del mraw, mout, parts
@@ -501,14 +502,14 @@ def run_ours(args):
                 codecs[f"{name}_block_compress"] = record(ms_c, B, U, cb, f"lz_encode_kernel<{name}>", traffic=ncu_traffic(f"{name}_block_compress", B))
                 ms_d = timed(lambda: ctx.decompress_batch(codec, capi.DEVICE, B, eslots, t_slot_off, t_ecl, out, t_raw_off, t_raw_len, t_dl, t_st))
                 assert int((t_st != 0).sum()) == 0 and bool(torch.equal(out, raw))
-                codecs[f"{name}_block_decompress_gpu_encoded"] = record(ms_d, B, U, cb, f"g4_kernel<{name}>", streams="this engine's GPU encoder",
+                codecs[f"{name}_block_decompress_gpu_encoded"] = record(ms_d, B, U, cb, f"{tpb or 'lz_decode_kernel'}<{name}>", streams="this engine's GPU encoder",
                                                                          traffic=ncu_traffic(f"{name}_block_decompress_gpu_encoded", B))
                 if name == "lz4":   # the headline already is snappy on CPU-encoder streams
                     lcomp, lcoff, lclen, lenc = compress_host(O_LZ4, data, B, U, nt)
                     t_lcomp, t_lco, t_lcl = torch.from_numpy(lcomp).to(dev), i64(lcoff), i64(lclen)
                     ms_d = timed(lambda: ctx.decompress_batch(codec, capi.DEVICE, B, t_lcomp, t_lco, t_lcl, out, t_raw_off, t_raw_len, t_dl, t_st))
                     assert int((t_st != 0).sum()) == 0 and bool(torch.equal(out, raw))
-                    codecs["lz4_block_decompress"] = record(ms_d, B, U, float(lclen.sum()), "g4_kernel<lz4>", traffic=ncu_traffic("lz4_block_decompress", B),
+                    codecs["lz4_block_decompress"] = record(ms_d, B, U, float(lclen.sum()), f"{tpb or 'lz_decode_kernel'}<lz4>", traffic=ncu_traffic("lz4_block_decompress", B),
                                                              streams="lz4 (Arrow's bundled liblz4, LZ4_compress_default) made on the host" if lenc == "stand-in" else "oracle/lz4.c encoder")
                     del t_lcomp
             except Exception as e:
@@ -578,7 +579,7 @@ def run_ours(args):
                 ms_r = timed(lambda: ctx.decompress_batch(codec, capi.DEVICE, n2, t_c, t_co, t_cl, out, t_do2, t_dc2, t_dl2, t_st2), k=3, warm=1)
                 got = out[: n2 * U].view(rep, nb * U)
                 assert int((t_st2 != 0).sum()) == 0 and bool(torch.equal(got[0], t_want)) and bool(torch.equal(got[rep - 1], t_want))
-                rc[f"{name}_block_decompress"] = record(ms_r, n2, U, float(ccl.sum()) * rep, f"g4_kernel<{name}>", encoder=cenc)
+                rc[f"{name}_block_decompress"] = record(ms_r, n2, U, float(ccl.sum()) * rep, f"{tpb or 'lz_decode_kernel'}<{name}>", encoder=cenc)
                 del t_c
             extras["real_corpus"] = rc
         except Exception as e:

@@ -69,7 +69,7 @@ int cj_ctx_create(int device, cj_ctx** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("CJ_DECODE_GEN")) c->decode_gen = atoi(v);
-    if (c->decode_gen != 2 && c->decode_gen != 4 && c->decode_gen != 7) c->decode_gen = 4;
+    if (c->decode_gen != 2 && c->decode_gen != 4 && c->decode_gen != 7) c->decode_gen = 7;
     if (const char* v = getenv("CJ_G4_MIN_UNITS")) c->g4_min_units = atol(v);
     // The thread-per-block decoder's far back-reference fetches are 16-byte reads scattered over 4 GiB of live windows:
     // with the default 64-byte L2 fetch granularity every miss drags a second, unused sector in from DRAM.
@@ -185,8 +185,9 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
     cudaEventRecord(c->ev0, c->stream);
     if (!compress) {
         if (codec == CJ_SNAPPY_RAW || codec == CJ_LZ4_BLOCK) {
-            // Large batches take the thread-per-block kernel (generation 4); everything else, and whatever it
-            // declines, the warp-per-block kernel (generation 2).  cj_ctx_set_decode_path() / CJ_DECODE_GEN select.
+            // Large batches take a thread-per-block kernel (generation 7; generation 4, DESIGN.md 4.7, on request);
+            // everything else, and whatever it declines, the warp-per-block kernel (generation 2).
+            // cj_ctx_set_decode_path() / CJ_DECODE_GEN select.
             if (c->decode_gen >= 4 && reset_counter && (long)b.n >= c->g4_min_units) {
                 e = c->decode_gen == 7 ? cj::launch_lz_decode7(codec, b, c->g4, c->sm_count, c->stream)
                                        : cj::launch_lz_decode4(codec, b, c->g4, c->sm_count, c->stream);

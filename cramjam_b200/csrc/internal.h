@@ -95,8 +95,8 @@ struct cj_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
-    int decode_gen = 4;            // LZ4/Snappy block decode path: 2 = one warp per block (lz_decode.cuh), 4 = one thread per block (lz_decode4.cu), the
-                                   // default for large batches
+    int decode_gen = 7;            // LZ4/Snappy block decode path for large batches: 2 = one warp per block (lz_decode.cuh), 4 = one thread per block with
+                                   // 8-byte chunks (lz_decode4.cu), 7 = one thread per block with 16-byte chunks and granule rings (lz_decode7.cu), the default
     long g4_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
     const unsigned* redo_ctr = nullptr;   // device counters of the most recent generation-4 launch ([1] = units handed to generation 2)
     bool redo_valid = false;

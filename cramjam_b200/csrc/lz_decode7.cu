@@ -12,8 +12,7 @@
 
 namespace cj {
 
-constexpr int G7_MAX_WARPS = 18;   // most warps per CTA (18 x 12 800 bytes of lane records fill the 227 KB); chosen at launch: one CTA per SM, as many warps as the batch needs
-static_assert(g7::cta_bytes(3, G7_MAX_WARPS) <= 232448 && g7::cta_bytes(2, G7_MAX_WARPS) <= 232448, "lane records of the largest CTA must fit the shared memory of an SM");
+constexpr int G7_MAX_WARPS = 20;   // most warps per CTA (640 threads x 102 registers); chosen at launch: one CTA per SM, as many warps as the batch needs
 
 struct G7 {
     uint32_t* redo_list;   // units for the generation-2 kernel
@@ -21,26 +20,23 @@ struct G7 {
 };
 
 // Memory operations of the lane program.  Shared-memory accesses are volatile asm on 32-bit shared addresses and keep their
-// program order; the asynchronous copies and the global stores are predicated PTX (no branch around them).
-//
-// Ordering of the far fetch (cp16_far_if): it reads, with cp.async.ca, output bytes that the SAME lane stored earlier with
-// st.global.v4 (stg128_if) — never another thread's.  The store precedes the fetch in program order, both are volatile asm with
-// a memory clobber and are issued by one warp through one LSU queue; the L1 is write-through and a store updates or evicts the
-// line it hits, which is what makes an ordinary ld.global after st.global by the same thread return the stored value, and
-// LDGSTS performs the same L1 lookup as LDG.  (The argument, and its evidence, are those of lz_decode4.cu.)
+// program order; predicated forms are predicated PTX (no branch around them).
 struct G7Env {
-    uint32_t in_l, st_l, asm_l, lut;
+    uint32_t in_l, out_l, st_l, lut;
     const Batch& b;
     const G7& g;
     uint32_t cur;
     __device__ __forceinline__ G7Env(const Batch& b_, const G7& g_) : b(b_), g(g_) {}
+    __device__ __forceinline__ void tick() const {}
     __device__ __forceinline__ uint32_t lds32(uint32_t a) const { return cj::lds32(a); }
     __device__ __forceinline__ uint32_t lds8(uint32_t a) const { return cj::lds8(a); }
-    __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) const { cj::sts32(a, v); }
     __device__ __forceinline__ g7::u4 lds128(uint32_t a) const {
         g7::u4 v;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
         return v;
+    }
+    __device__ __forceinline__ void sts128(uint32_t a, g7::u4 v) const {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
     __device__ __forceinline__ void sts128_if(uint32_t a, g7::u4 v, bool p) const {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)p) : "memory");
@@ -48,11 +44,16 @@ struct G7Env {
     __device__ __forceinline__ void stg128_if(uint8_t* p, g7::u4 v, bool pred) const {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
     }
-    __device__ __forceinline__ void stg8(uint8_t* p, uint32_t v) const { *p = (uint8_t)v; }
-    __device__ __forceinline__ uint32_t ldg8(const uint8_t* p) const { return ldg_u8(p); }
+    // Far source granule.  cp.async.ca (LDGSTS, L1-allocating) reads output bytes that the SAME lane stored earlier with
+    // st.global.v4 (stg128_if) — never another thread's.  The store precedes the fetch in program order, both are volatile asm with
+    // a memory clobber and are issued by one warp through one LSU queue; the L1 is write-through and a store updates or evicts the
+    // line it hits, which is what makes an ordinary ld.global after st.global by the same thread return the stored value, and
+    // LDGSTS performs the same L1 lookup as LDG.  (The argument, and its evidence, are those of lz_decode4.cu.)
     __device__ __forceinline__ void cp16_far_if(uint32_t saddr, const uint8_t* gptr, bool pred) const {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16;\n\t}" ::"r"(saddr), "l"(gptr), "r"((uint32_t)pred) : "memory");
     }
+    __device__ __forceinline__ void stg8(uint8_t* p, uint32_t v) const { *p = (uint8_t)v; }
+    __device__ __forceinline__ uint32_t ldg8(const uint8_t* p) const { return ldg_u8(p); }
     __device__ __forceinline__ void cp16_in_if(uint32_t saddr, const uint8_t* gptr, uint32_t ssz, bool pred) const {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(saddr), "l"(gptr), "r"(ssz), "r"((uint32_t)pred) : "memory");
     }
@@ -76,10 +77,10 @@ __global__ void __launch_bounds__(G7_MAX_WARPS * 32, 1) g7_kernel(Batch b, G7 g)
     const int warps = blockDim.x >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G7Env env(b, g);
-    const uint32_t rec = smem_addr(smem) + (uint32_t)warp * g7::warp_bytes(D) + (uint32_t)lane * g7::lane_stride(D);
-    env.in_l = rec + 16;
-    env.st_l = rec + g7::IN_SLOT;
-    env.asm_l = rec + g7::IN_SLOT + (uint32_t)D * g7::ST_SLOT;
+    const uint32_t wbase = smem_addr(smem) + (uint32_t)warp * g7::warp_bytes(D);
+    env.in_l = wbase + (uint32_t)lane * 16;                                       // granule q of the lane's input ring: in_l + q * 512
+    env.out_l = wbase + g7::IN_G * g7::GROW + (uint32_t)lane * 16;                // ... of its output ring: out_l + q * 512
+    env.st_l = wbase + (g7::IN_G + g7::OUT_G) * g7::GROW + (uint32_t)lane * 16;   // ... of the staging pair of slot u: st_l + (2u + q) * 512
     env.lut = smem_addr(smem) + (uint32_t)warps * g7::warp_bytes(D);
     if (CODEC == CJ_SNAPPY_RAW) {
         for (uint32_t t = threadIdx.x; t < 256; t += blockDim.x) sts32(env.lut + 4 * t, g7::tag_entry(t));
@@ -142,7 +143,7 @@ static cudaError_t launch_g7(const Batch& b, const G7& g, int sm_count, cudaStre
 
 cudaError_t launch_lz_decode7(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream) {
     const char* de = getenv("CJ_G7_D");   // experiments: chunks in flight per lane (read per launch)
-    const int depth = de ? atoi(de) : 3;
+    const int depth = de ? atoi(de) : 2;
     const size_t n = b.n;
     if (sc.ensure_fixed((n + 8) * 4 + 64) != 0) return cudaErrorMemoryAllocation;
     G7 g;
@@ -150,8 +151,8 @@ cudaError_t launch_lz_decode7(int codec, const Batch& b, LzScratch& sc, int sm_c
     g.redo_list = (uint32_t*)sc.fixed() + 8;
     cudaError_t e = cudaMemsetAsync(g.ctr, 0, 4 * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
-    if (codec == CJ_LZ4_BLOCK) e = depth <= 2 ? launch_g7<CJ_LZ4_BLOCK, 2>(b, g, sm_count, stream) : launch_g7<CJ_LZ4_BLOCK, 3>(b, g, sm_count, stream);
-    else e = depth <= 2 ? launch_g7<CJ_SNAPPY_RAW, 2>(b, g, sm_count, stream) : launch_g7<CJ_SNAPPY_RAW, 3>(b, g, sm_count, stream);
+    if (codec == CJ_LZ4_BLOCK) e = depth <= 2 ? launch_g7<CJ_LZ4_BLOCK, 2>(b, g, sm_count, stream) : (depth == 3 ? launch_g7<CJ_LZ4_BLOCK, 3>(b, g, sm_count, stream) : launch_g7<CJ_LZ4_BLOCK, 4>(b, g, sm_count, stream));
+    else e = depth <= 2 ? launch_g7<CJ_SNAPPY_RAW, 2>(b, g, sm_count, stream) : (depth == 3 ? launch_g7<CJ_SNAPPY_RAW, 3>(b, g, sm_count, stream) : launch_g7<CJ_SNAPPY_RAW, 4>(b, g, sm_count, stream));
     if (e != cudaSuccess) return e;
     return launch_lz_decode_list(codec, b, g.redo_list, g.ctr, sm_count, stream);
 }

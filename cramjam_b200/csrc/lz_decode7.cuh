@@ -4,26 +4,30 @@
 // Reference entry points: snap::raw::Decoder::decompress behind cramjam.snappy.decompress_raw / decompress_raw_into
 // (src/snappy.rs:52-60,102-108) and LZ4_decompress_safe behind lz4::block::decompress_into (src/lz4.rs:78-95,140-173).
 //
-// One THREAD per block, like generation 4 (lz_decode4.cu), rebuilt around its two measured costs (229 warp
-// instructions per <= 8-byte chunk, integer pipe 76 % busy):
+// One THREAD per block, like generation 4 (lz_decode4.cu), rebuilt around what ncu showed of it and of this kernel's first
+// version (profiles/r02_g7_*): with 65 536 lanes at unrelated positions the kernel is bound by the SM's L1 / shared-memory
+// data pipe — one wavefront per cycle, and a scattered 4-byte or 16-byte access of a warp costs a wavefront per bank conflict
+// or per cache line — long before it is bound by instruction issue.  So every access is made as wide and as conflict-free as
+// the format allows:
 //
-//   * CHUNKS are up to 16 bytes (9 900 instead of 12 600 sub-iterations per 64 KiB block of the bench corpus);
-//   * every per-lane shared-memory structure is LINEAR in the lane's own record, so a chunk's source is one byte address
-//     computed when the chunk is issued and its six source words are read at immediate offsets from it:
-//       - the 128-byte input ring carries a 32-byte copy of its head behind its end (written by the same cp.async group), so a
-//         24-byte read never wraps;
-//       - a far back-reference is fetched from the block's own output in global memory by one or two 16-byte cp.async into a
-//         48-byte staging slot (16 bytes of slack in front of the data);
-//       - the output is assembled in a 64-byte window [P1][P0][A][B]: A is the 16-byte granule being filled, B takes what
-//         spills over, P1/P0 are the two granules before A.  When A is complete it is stored with one st.global.v4 and the
-//         window moves down by one granule.  Back-references of at most 32 bytes are read straight from the window when the
-//         chunk retires (no stall, and short periods double: 1, 2, 4, 8, 16 bytes per chunk);
+//   * CHUNKS are up to 16 bytes (9 900 instead of 12 600 iterations per 64 KiB block of the bench corpus);
+//   * every per-lane structure in shared memory is a ring of 16-byte GRANULES, interleaved across the lanes of the warp
+//     (granule q of lane l at q * 512 + l * 16): a 16-byte access of a quarter warp then touches each bank once, whatever
+//     granule each lane is at.  The input ring has 8 granules (filled by 16-byte cp.async, two per pass), the ring of recent
+//     output 4, and every chunk in flight owns a staging pair;
+//   * a chunk's SOURCE is always two granules, read with two ld.shared.v4 into eight registers when the chunk retires: from the
+//     input ring (literal bytes), from the output ring (back-references of at most 32 bytes), or from the chunk's staging pair,
+//     which one or two 16-byte cp.async filled from the block's own output in global memory one pass earlier (everything
+//     further back).  A two-stage select picks the six words the chunk starts in, five funnel shifts align them to the output
+//     phase.  (Fetching far sources with ld.global straight into the registers was measured and is slower: the loads of
+//     different slots share hardware scoreboards, so waiting for the oldest waits for the newest, profiles/README.md.)
+//   * the OUTPUT is assembled in registers: a second two-stage select places the five words at the output position inside a
+//     32-byte window whose lower half is the granule being filled; a finished granule is stored with one st.global.v4.  The
+//     partial granule is mirrored into the output ring every iteration, which is all a near back-reference needs;
 //   * a back-reference further than 32 bytes whose source is not yet in global memory waits for it (the chunk shrinks to what
-//     is there, or the lane issues nothing for an iteration) instead of carrying a third source path through every chunk;
-//   * retire does no source-kind dispatch at all: load six words, five funnel shifts, merge the first word with the bytes
-//     already in the window, five word stores, the granule hand-over;
+//     is there, or the lane issues nothing for an iteration); short periods double (1, 2, 4, 8, 16 bytes per chunk);
 //   * the last input granule is fetched with cp.async's src-size operand (the bytes beyond the block arrive as zeros), so the
-//     end of the input needs no separate path.
+//     end of the input needs no separate path and nothing beyond the unit is read.
 //
 // Everything unusual (literal with length bytes, LZ4 length runs, the LZ4 end-of-block zone) takes one slow branch that
 // decodes from global memory with the oracle's rules; whatever fails a check, and every unit that is not 16-byte aligned,
@@ -41,18 +45,14 @@ namespace cj {
 namespace g7 {
 
 constexpr int CODEC_SNAPPY = 0, CODEC_LZ4 = 2;   // = CJ_SNAPPY_RAW, CJ_LZ4_BLOCK (include/cramjam_cuda.h)
-constexpr uint32_t INB = 128;            // input ring bytes per lane
-constexpr uint32_t IN_SLOT = 16 + INB + 32;   // 16 bytes of slack in front, the copy of the ring's first 32 bytes behind
-constexpr uint32_t ST_SLOT = 48;         // staging slot of one far chunk: 16 bytes of slack + two 16-byte granules
-constexpr uint32_t ASM_SLOT = 80;        // 16 bytes of slack + [P1][P0][A][B]
-constexpr uint32_t ASM_P1 = 16, ASM_P0 = 32, ASM_A = 48, ASM_B = 64;
-constexpr uint32_t NEAR = 32;            // back-references up to this offset are read from the assembly window at retire time
+constexpr uint32_t IN_G = 8;             // input ring granules per lane
+constexpr uint32_t INB = IN_G * 16;      // input ring bytes per lane
+constexpr uint32_t OUT_G = 4;            // granules of recent output per lane: the one being filled, two behind it, one ahead
+constexpr uint32_t GROW = 512;           // bytes between consecutive granules of one lane (32 lanes x 16 bytes)
+constexpr uint32_t NEAR = 32;            // back-references up to this offset are read from the output ring at retire time
 constexpr uint32_t MAXU = 1u << 30;
-constexpr uint32_t lane_payload(int D) { return IN_SLOT + (uint32_t)D * ST_SLOT + ASM_SLOT; }
-// lane records are 16 bytes (mod 128) apart: same-offset 16-byte accesses of a quarter warp fall into different banks
-constexpr uint32_t lane_stride(int D) { return lane_payload(D) + (16u + 128u - lane_payload(D) % 128u) % 128u; }
-constexpr uint32_t warp_bytes(int D) { return 32u * lane_stride(D); }
-constexpr uint32_t cta_bytes(int D, int warps) { return warp_bytes(D) * (uint32_t)warps + 1024u + 64u; }   // + the 256-entry tag table + slack behind the last record
+constexpr uint32_t warp_bytes(int D) { return (IN_G + OUT_G + 2u * (uint32_t)D) * GROW; }   // + a staging pair per chunk in flight
+constexpr uint32_t cta_bytes(int D, int warps) { return warp_bytes(D) * (uint32_t)warps + 1024u; }   // + the 256-entry tag table
 
 struct u4 {
     uint32_t x, y, z, w;
@@ -66,7 +66,15 @@ G7_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {   // ((hi:lo) >
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
+G7_HD uint32_t low_bits(uint32_t nbits) {   // mask of the low min(nbits, 32) bits
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, nbits);
+#else
+    return nbits >= 32u ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+#endif
+}
 G7_HD uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+G7_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
 
 // Snappy tag table: [6:0] compressed size of the element, [14:8] bytes it produces, [23:22] kind, [21:16] field,
 // bit 31 = not a plain element (literal with length bytes, 4-byte-offset copy).
@@ -83,15 +91,15 @@ G7_HD uint32_t tag_entry(uint32_t tag) {
 }
 
 // The program of one lane over one block.  `Env` supplies the memory operations (shared-memory accesses by 32-bit address,
-// predicated cp.async / global stores, the warp vote) and the per-lane record addresses in_l / st_l / asm_l and the tag table
-// lut.  has == false: the lane has no block and only keeps step with its warp.
+// predicated stores, cp.async, the warp vote), the addresses in_l / out_l / st_l of granule 0 of the lane's input ring,
+// output ring and staging pairs, and the tag table lut.  has == false: the lane has no block and only keeps step with its warp.
 //
 // One PASS of the loop is D iterations (slots u = 0..D-1, unrolled); an iteration retires the chunk issued into its slot one
 // pass earlier and issues a new one.  Each iteration commits one cp.async group, so wait_group(D-1) at its top guarantees
 // everything issued one pass ago.  The input ring is refilled once per pass, two granules at a time.
 template <int CODEC, int D, class Env>
 G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, uint64_t sl, uint64_t dcap) {
-    const uint32_t in_l = env.in_l, st_l = env.st_l, asm_l = env.asm_l, lut = env.lut;
+    const uint32_t in_l = env.in_l, out_l = env.out_l, st_l = env.st_l, lut = env.lut;
     constexpr uint32_t RUN = 0, DRAIN = 1, IDLE = 2;   // decoding / input consumed, chunks still in flight / nothing to do
     uint32_t st = IDLE;
     uint32_t n = 0, ulen = 0, ip = 0;
@@ -118,7 +126,7 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
         else env.redo();
     }
     const uint32_t nload = st == RUN ? ((n + 31u) & ~31u) : 0u;   // granule pairs are requested up to here; bytes beyond n arrive as zeros
-    uint32_t loaded = 0, lim = 0, lnext = 0;   // input bytes requested / known to have arrived / requested one pass ago
+    uint32_t loaded = 0, lim = 0, lnext = 0;   // input bytes requested / known to have arrived in the ring / requested one pass ago
     uint32_t opi = 0, opr = 0;       // output position of the next chunk to issue / to retire
     uint32_t rem = 0, sp = 0;        // bytes of the current element still to issue; literal: input position, copy: (effective) offset
     bool is_lit = false;
@@ -126,46 +134,59 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
     uint32_t lz_ml = 0;                       // LZ4: match-length nibble of the token whose literals are being issued
     uint32_t tw0 = 0, tw1 = 0;       // the two ring words around ip, fetched one iteration ahead
     bool tw_ok = false;              // ... and whether they had arrived when they were fetched
-    uint32_t M[D], P[D];             // chunk in flight: bytes, shared-memory byte address of its source
-    uint32_t IPH[D];                 // lowest input position the decoder needed when the slot was issued (its literal chunk reads no lower)
+    u4 acc = {0, 0, 0, 0};           // the output granule being filled: bytes [opr & ~15, opr)
+    // chunk in flight, per slot: M = bytes | (byte offset of its source window in the first granule) << 8;
+    // G = shared-memory addresses of its two source granules (>> 4, 16 bits each)
+    uint32_t M[D], G[D], IPH[D];
 #pragma unroll
-    for (int u = 0; u < D; u++) { M[u] = 0; P[u] = asm_l + ASM_A; IPH[u] = 0; }
+    for (int u = 0; u < D; u++) { M[u] = 0; G[u] = (out_l >> 4) | ((out_l >> 4) << 16); IPH[u] = 0; }
 
     while (env.any(st != IDLE)) {
 #pragma unroll
         for (int u = 0; u < D; u++) {
+            env.tick();
             env.template wait<D - 1>();
-            if (u == 0) lim = lnext;   // the pairs requested one pass ago have arrived
-            const uint32_t st_u = st_l + (uint32_t)u * ST_SLOT;
-            // ---- loads first (shared-memory accesses keep their program order): the six source words of the chunk issued one
-            //      pass ago, the window word it starts in, and the table entry of the tag fetched one iteration ago ----
-            const uint32_t c = M[u], a = P[u];
-            const uint32_t a0 = a & ~3u;
-            const uint32_t wa = asm_l + ASM_A + (opr & 12u);
-            const uint32_t s0 = env.lds32(a0), s1 = env.lds32(a0 + 4), s2 = env.lds32(a0 + 8), s3 = env.lds32(a0 + 12), s4 = env.lds32(a0 + 16),
-                           s5 = env.lds32(a0 + 20);
-            const uint32_t w = env.lds32(wa);
+            if (u == 0) lim = lnext;   // the pair requested one pass ago has arrived
+            // ---- loads first: the two source granules of the chunk issued one pass ago, and the table entry of the tag fetched one
+            //      iteration ago ----
+            const uint32_t m = M[u];
+            const uint32_t c = m & 31u, d = m >> 8;
+            const u4 sa = env.lds128((G[u] & 0xFFFFu) << 4), sb = env.lds128((G[u] >> 16) << 4);
             const uint32_t t = funnel_r(tw0, tw1, ip * 8u);   // the funnel shift takes its amount mod 32
             uint32_t ent = 0;
             if (CODEC == CODEC_SNAPPY) ent = env.lds32(lut + 4u * (t & 255u));
-            // ---- retire: align to the output phase, merge with the bytes already in the window, store five words ----
+            // ---- retire: pick the six words the source window starts in, align them to the output phase, place them behind the
+            //      bytes of the granule being filled ----
             {
-                const uint32_t sh = a * 8u;
-                uint32_t x0 = funnel_r(s0, s1, sh);
-                const uint32_t x1 = funnel_r(s1, s2, sh), x2 = funnel_r(s2, s3, sh), x3 = funnel_r(s3, s4, sh), x4 = funnel_r(s4, s5, sh);
-                const uint32_t hm = 0xFFFFFFFFu << ((opr * 8u) & 31u);   // bytes of the first word that are not output yet
-                x0 = (x0 & hm) | (w & ~hm);
-                env.sts32(wa, x0);
-                env.sts32(wa + 4, x1);
-                env.sts32(wa + 8, x2);
-                env.sts32(wa + 12, x3);
-                env.sts32(wa + 16, x4);   // bytes beyond opr + c are not output yet: whatever lands there is overwritten later
-                const bool cross = (opr & 15u) + c >= 16u;   // granule A is complete: store it, move the window down
-                const u4 vp = env.lds128(asm_l + ASM_P0), va = env.lds128(asm_l + ASM_A), vb = env.lds128(asm_l + ASM_B);
-                env.stg128_if(dst + (opr & ~15u), va, cross);
-                env.sts128_if(asm_l + ASM_P1, vp, cross);
-                env.sts128_if(asm_l + ASM_P0, va, cross);
-                env.sts128_if(asm_l + ASM_A, vb, cross);
+                const bool w1 = (d & 4u) != 0, w2 = (d & 8u) != 0;
+                const uint32_t u0 = w1 ? sa.y : sa.x, u1 = w1 ? sa.z : sa.y, u2 = w1 ? sa.w : sa.z, u3 = w1 ? sb.x : sa.w, u4_ = w1 ? sb.y : sb.x,
+                               u5 = w1 ? sb.z : sb.y, u6 = w1 ? sb.w : sb.z, u7 = sb.w;
+                const uint32_t t0 = w2 ? u2 : u0, t1 = w2 ? u3 : u1, t2 = w2 ? u4_ : u2, t3 = w2 ? u5 : u3, t4 = w2 ? u6 : u4_, t5 = w2 ? u7 : u5;
+                const uint32_t sh = d * 8u;
+                const uint32_t x0 = funnel_r(t0, t1, sh), x1 = funnel_r(t1, t2, sh), x2 = funnel_r(t2, t3, sh), x3 = funnel_r(t3, t4, sh),
+                               x4 = funnel_r(t4, t5, sh);
+                // x0..x4 hold the chunk from byte (opr & 3) of x0 on; word j of the 32-byte window takes x[j - wo], wo = word of opr
+                const bool o1 = (opr & 4u) != 0, o2 = (opr & 8u) != 0;
+                const uint32_t z0 = x0, z1 = o1 ? x0 : x1, z2 = o1 ? x1 : x2, z3 = o1 ? x2 : x3, z4 = o1 ? x3 : x4, z5 = x4;
+                const uint32_t y0 = z0, y1 = z1, y2 = o2 ? z0 : z2, y3 = o2 ? z1 : z3, y4 = o2 ? z2 : z4, y5 = o2 ? z3 : z5, y6 = z4, y7 = z5;
+                // bytes below opr come from the accumulator
+                const int32_t ob = (int32_t)((opr & 15u) * 8u);
+                const uint32_t m0 = low_bits((uint32_t)ob), m1 = low_bits((uint32_t)imax(ob - 32, 0)), m2 = low_bits((uint32_t)imax(ob - 64, 0)),
+                               m3 = low_bits((uint32_t)imax(ob - 96, 0));
+                u4 lo;
+                lo.x = (acc.x & m0) | (y0 & ~m0);
+                lo.y = (acc.y & m1) | (y1 & ~m1);
+                lo.z = (acc.z & m2) | (y2 & ~m2);
+                lo.w = (acc.w & m3) | (y3 & ~m3);
+                const bool cross = (opr & 15u) + c >= 16u;   // the granule is complete: store it, go on with the upper half
+                const uint32_t ga = out_l + ((opr >> 4) & (OUT_G - 1)) * GROW, gb = out_l + (((opr >> 4) + 1u) & (OUT_G - 1)) * GROW;
+                env.stg128_if(dst + (opr & ~15u), lo, cross);
+                acc.x = cross ? y4 : lo.x;
+                acc.y = cross ? y5 : lo.y;
+                acc.z = cross ? y6 : lo.z;
+                acc.w = cross ? y7 : lo.w;
+                env.sts128(ga, lo);   // the output ring always holds the granule being filled as far as it is known
+                env.sts128_if(gb, acc, cross);
                 opr += c;
             }
             // ---- decode the next element if the current one is fully issued ----
@@ -221,18 +242,27 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const uint32_t F = opr & ~15u;            // output below F is in global memory
                 const bool isnear = sp <= NEAR;
                 IPH[u] = (is_lit && rem != 0) ? sp : ip;
+                // the source window starts k bytes before the source (those bytes are replaced by the accumulator's): its position
+                // in the input (literal) or in the output (copy), and the offset of its first byte in the first of its two granules
+                const uint32_t sk = (is_lit ? sp : fs) - k;
+                const uint32_t dd = sk & 15u;
                 // bytes the source can supply now: literal bytes that have arrived / a near copy never overlaps its own source (a
-                // short period doubles below) / the part of a far source that is in global memory already
+                // short period doubles below) / the part of a far source that is in global memory already; and a chunk never
+                // reaches beyond its two granules
                 const int32_t avail = (int32_t)(is_lit ? lim - sp : (isnear ? sp : F - fs));
-                const uint32_t cn = avail <= 0 ? 0u : umin(c16, (uint32_t)avail);
+                const uint32_t cn = avail <= 0 ? 0u : umin(umin(c16, (uint32_t)avail), 32u - dd - k);
                 const bool isfar = !is_lit && !isnear && cn != 0;
-                const uint8_t* gp = dst + (fs & ~15u);
-                env.cp16_far_if(st_u + 16, gp, isfar);
-                env.cp16_far_if(st_u + 32, gp + 16, isfar && (fs & 15u) + cn > 16u);   // second granule only if the chunk reaches into it
-                const uint32_t base = is_lit ? in_l : (isnear ? asm_l + ASM_A : st_u + 16);
-                const uint32_t boff = is_lit ? (sp & (INB - 1)) : (isnear ? (opi & 15u) - sp : (fs & 15u));
-                P[u] = base + boff - k;
-                M[u] = cn;
+                const int32_t g0 = (int32_t)(sk & ~15u);   // far: output position of the first source granule (-16: in front of the block)
+                const uint32_t s0 = st_l + 2u * (uint32_t)u * GROW;   // ... and this slot's staging pair
+                env.cp16_far_if(s0, dst + (g0 < 0 ? 0 : g0), isfar && g0 >= 0);
+                env.cp16_far_if(s0 + GROW, dst + (g0 + 16), isfar && dd + k + cn > 16u);   // second granule only if the chunk reaches into it
+                const uint32_t rbase = is_lit ? in_l : out_l;
+                const uint32_t rmask = is_lit ? (IN_G - 1) : (OUT_G - 1);
+                const uint32_t gi = sk >> 4;
+                const bool ring = is_lit || isnear;
+                const uint32_t a0 = ring ? rbase + (gi & rmask) * GROW : s0, a1 = ring ? rbase + ((gi + 1u) & rmask) * GROW : s0 + GROW;
+                G[u] = (a0 >> 4) | ((a1 >> 4) << 16);
+                M[u] = cn | (dd << 8);
                 sp = is_lit ? sp + cn : ((cn == sp && sp < 16u) ? sp + sp : sp);
                 opi += cn;
                 rem -= cn;
@@ -306,23 +336,24 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 }
             }
             // ---- fetch the tag words of the next element; their latency overlaps the loop bookkeeping ----
-            tw0 = env.lds32(in_l + (ip & (INB - 4)));
-            tw1 = env.lds32(in_l + (ip & (INB - 4)) + 4);
-            tw_ok = umin(ip + 4u, nload) <= lim;
+            {
+                const uint32_t w0 = ip >> 2, w1 = w0 + 1u;
+                tw0 = env.lds32(in_l + ((w0 >> 2) & (IN_G - 1)) * GROW + (w0 & 3u) * 4u);
+                tw1 = env.lds32(in_l + ((w1 >> 2) & (IN_G - 1)) * GROW + (w1 & 3u) * 4u);
+                tw_ok = umin(ip + 4u, nload) <= lim;
+            }
             // ---- input ring, once per pass: one more pair of granules if it fits ahead of everything still needed ----
             if (u == 0) {
                 const uint32_t low = IPH[(u + 1) % D];   // the oldest slot in flight: no chunk in flight reads input below this (less 3 bytes)
                 const uint32_t keep = (low < 3u ? 0u : low - 3u) & ~15u;
                 const bool go = st == RUN && loaded < nload && loaded + 32u <= keep + INB;
-                const uint32_t rpos = loaded & (INB - 1);
+                const uint32_t ra = in_l + ((loaded >> 4) & (IN_G - 1)) * GROW;   // loaded is a multiple of 32: the pair does not wrap
                 const uint32_t left = n - loaded;   // >= 1 when go
                 const uint32_t z1 = umin(left, 16u), z2 = left > 16u ? umin(left - 16u, 16u) : 0u;   // bytes beyond the block are zero-filled, not read
                 const uint8_t* g1 = src + loaded;
                 const uint8_t* g2 = g1 + (left > 16u ? 16u : 0u);
-                env.cp16_in_if(in_l + rpos, g1, z1, go);
-                env.cp16_in_if(in_l + rpos + 16, g2, z2, go);
-                env.cp16_in_if(in_l + INB, g1, z1, go && rpos == 0);        // the copy of the ring's head behind its end
-                env.cp16_in_if(in_l + INB + 16, g2, z2, go && rpos == 0);
+                env.cp16_in_if(ra, g1, z1, go);
+                env.cp16_in_if(ra + GROW, g2, z2, go);
                 loaded += go ? 32u : 0u;
                 lnext = loaded;   // this pair joins the group committed below: it has arrived when the next pass begins
             }
@@ -332,12 +363,13 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
         if (st == DRAIN) {
             bool empty = true;
 #pragma unroll
-            for (int u = 0; u < D; u++) empty = empty && M[u] == 0;
+            for (int u = 0; u < D; u++) empty = empty && (M[u] & 31u) == 0;
             if (empty) {
                 if (CODEC == CODEC_SNAPPY && opi != ulen) env.redo();
                 else {
-                    const uint32_t k = opr & 15u;   // the bytes of the unfinished granule A
-                    for (uint32_t j = 0; j < k; j++) env.stg8(dst + (opr & ~15u) + j, env.lds8(asm_l + ASM_A + j));
+                    const uint32_t k = opr & 15u;   // the bytes of the unfinished granule
+                    const uint32_t ga = out_l + ((opr >> 4) & (OUT_G - 1)) * GROW;
+                    for (uint32_t j = 0; j < k; j++) env.stg8(dst + (opr & ~15u) + j, env.lds8(ga + j));
                     env.finish_ok(opi);
                 }
                 st = IDLE;

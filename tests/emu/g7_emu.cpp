@@ -19,7 +19,7 @@ using cj::g7::u4;
 
 struct HostEnv {
     std::vector<uint8_t> smem;
-    uint32_t in_l, st_l, asm_l, lut;
+    uint32_t in_l, out_l, st_l, lut;
     int mode;
     struct Cp {
         uint32_t saddr;
@@ -43,6 +43,7 @@ struct HostEnv {
     bool ok_range(uint32_t a, uint32_t n, uint32_t align) {
         if ((a & (align - 1)) != 0) { fail(1); return false; }
         if ((uint64_t)a + n > smem.size()) { fail(2); return false; }
+        if (a < lut && (a % cj::g7::GROW) + n > 16) { fail(10); return false; }   // a lane stays inside its own 16-byte column of the granule rows
         return true;
     }
     uint32_t lds32(uint32_t a) {
@@ -65,6 +66,8 @@ struct HostEnv {
         memcpy(&v, &smem[a], 16);
         return v;
     }
+    void tick() { iters++; }
+    void sts128(uint32_t a, u4 v) { sts128_if(a, v, true); }
     void sts128_if(uint32_t a, u4 v, bool p) {
         if (!p) return;
         if (!ok_range(a, 16, 16)) return;
@@ -114,7 +117,6 @@ struct HostEnv {
         push(saddr, tmp);
     }
     void commit() {
-        iters++;
         if (mode != 0) {
             groups.push_back(cur);
             cur.clear();
@@ -142,13 +144,13 @@ struct HostEnv {
 template <int CODEC, int D>
 long run(const uint8_t* src, uint32_t n, uint8_t* dst, uint64_t cap, int mode, int extra, long* stats) {
     HostEnv env;
-    const uint32_t rec = cj::g7::lane_stride(D);
-    env.smem.resize(rec + 1024 + 64);
+    const uint32_t rec = cj::g7::warp_bytes(D);   // the emulated lane is lane 0 of its warp; the other lanes' granules stay untouched
+    env.smem.resize(rec + 1024);
     uint32_t seed = 0x1234567u + n;
     for (auto& b : env.smem) { seed = seed * 1664525u + 1013904223u; b = (uint8_t)(seed >> 24); }   // nothing may rely on initial contents
-    env.in_l = 16;
-    env.st_l = cj::g7::IN_SLOT;
-    env.asm_l = cj::g7::IN_SLOT + D * cj::g7::ST_SLOT;
+    env.in_l = 0;
+    env.out_l = cj::g7::IN_G * cj::g7::GROW;
+    env.st_l = (cj::g7::IN_G + cj::g7::OUT_G) * cj::g7::GROW;
     env.lut = rec;
     for (uint32_t t = 0; t < 256; t++) {
         const uint32_t e = cj::g7::tag_entry(t);
