@@ -382,7 +382,7 @@ def run_ours(args):
     clocks = sampler.stop(wall0, wall1) if sampler else None
     total_blocks = B * world
     gen, min_units = ctx.decode_path()
-    tpb = f"g{gen}_kernel" if (gen in (4, 7) and B >= min_units) else None   # the thread-per-block kernel that decodes batches of this size
+    tpb = f"g{gen}_kernel" if (gen in (4, 7) and B >= min_units + min_units // 2) else None   # the thread-per-block kernel that decodes batches of this size
     kernel_name = f"{tpb}<snappy> (one thread per block) + lz_decode_list_kernel (redo list)" if tpb else "lz_decode_kernel<snappy, lane-parallel> (one warp per block)"
     value = total_blocks * U / (ms_dev * 1e6)
     alg_bytes = float(clen.sum()) + float(B) * U   # per launch on this rank: compressed read + uncompressed written

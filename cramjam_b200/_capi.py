@@ -147,7 +147,7 @@ class Context:
     def synchronize(self):
         _check(lib().cj_ctx_synchronize(self._h))
 
-    def set_decode_path(self, generation, min_units=32768):
+    def set_decode_path(self, generation, min_units=16384):
         """LZ4 / Snappy block decode kernels for batches of >= min_units units: 2 = one warp per block, 4 = one thread per
         block with 8-byte chunks (lz_decode4.cu), 7 = one thread per block with 16-byte chunks and linear per-lane records
         (lz_decode7.cu)."""

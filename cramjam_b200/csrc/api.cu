@@ -188,7 +188,8 @@ static int run_device(cj_ctx* c, int codec, bool compress, const cj::Batch& b, c
             // Large batches take a thread-per-block kernel (generation 7; generation 4, DESIGN.md 4.7, on request);
             // everything else, and whatever it declines, the warp-per-block kernel (generation 2).
             // cj_ctx_set_decode_path() / CJ_DECODE_GEN select.
-            if (c->decode_gen >= 4 && reset_counter && (long)b.n >= c->g4_min_units) {
+            const long tpb_min = codec == CJ_LZ4_BLOCK ? c->g4_min_units + c->g4_min_units / 2 : c->g4_min_units;
+            if (c->decode_gen >= 4 && reset_counter && (long)b.n >= tpb_min) {
                 e = c->decode_gen == 7 ? cj::launch_lz_decode7(codec, b, c->g4, c->sm_count, c->stream)
                                        : cj::launch_lz_decode4(codec, b, c->g4, c->sm_count, c->stream);
                 c->redo_ctr = (const unsigned*)c->g4.fixed();   // lz_decode4.cu keeps its counters at the start of the scratch

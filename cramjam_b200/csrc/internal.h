@@ -97,7 +97,8 @@ struct cj_ctx {
     uint64_t launches = 0;
     int decode_gen = 7;            // LZ4/Snappy block decode path for large batches: 2 = one warp per block (lz_decode.cuh), 4 = one thread per block with
                                    // 8-byte chunks (lz_decode4.cu), 7 = one thread per block with 16-byte chunks and granule rings (lz_decode7.cu), the default
-    long g4_min_units = 32768;     // smallest batch that leaves generation 2 (the thread-per-block kernel has a ~4.6 ms latency floor per 64 KiB block)
+    long g4_min_units = 16384;     // smallest Snappy batch that leaves generation 2; LZ4 batches need half as many again (a lane needs ~3.4 ms / ~4.5 ms for a
+                                   // 64 KiB Snappy / LZ4 block however small the batch: measured crossovers ~14 000 and ~22 000 blocks, profiles/README.md)
     const unsigned* redo_ctr = nullptr;   // device counters of the most recent generation-4 launch ([1] = units handed to generation 2)
     bool redo_valid = false;
     std::mutex mu;

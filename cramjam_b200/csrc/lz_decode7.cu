@@ -12,7 +12,8 @@
 
 namespace cj {
 
-constexpr int G7_MAX_WARPS = 20;   // most warps per CTA (640 threads x 102 registers); chosen at launch: one CTA per SM, as many warps as the batch needs
+constexpr int G7_MAX_WARPS = 20;   // most warps per CTA (640 threads x 102 registers); fewer if the lane records of 20 warps do not fit the SM's shared memory
+constexpr int g7_max_warps(int D) { return (int)((232448u - 1024u) / g7::warp_bytes(D)) < G7_MAX_WARPS ? (int)((232448u - 1024u) / g7::warp_bytes(D)) : G7_MAX_WARPS; }
 
 struct G7 {
     uint32_t* redo_list;   // units for the generation-2 kernel
@@ -43,6 +44,10 @@ struct G7Env {
     }
     __device__ __forceinline__ void stg128_if(uint8_t* p, g7::u4 v, bool pred) const {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
+    }
+    // two finished granules that make up one 32-byte sector leave with one 256-bit store: half as many write transactions
+    __device__ __forceinline__ void stg256_if(uint8_t* p, g7::u4 a, g7::u4 c, bool pred) const {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n\t}" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w), "r"((uint32_t)pred) : "memory");
     }
     // Far source granule.  cp.async.ca (LDGSTS, L1-allocating) reads output bytes that the SAME lane stored earlier with
     // st.global.v4 (stg128_if) — never another thread's.  The store precedes the fetch in program order, both are volatile asm with
@@ -112,7 +117,7 @@ static cudaError_t launch_g7(const Batch& b, const G7& g, int sm_count, cudaStre
     static cj_per_device_flag attr_flag;
     int& attr_done = attr_flag.here();
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(g7_kernel<CODEC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g7::cta_bytes(D, G7_MAX_WARPS));
+        cudaError_t e = cudaFuncSetAttribute(g7_kernel<CODEC, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g7::cta_bytes(D, g7_max_warps(D)));
         if (e != cudaSuccess) return e;
         attr_done = 1;
     }
@@ -121,10 +126,11 @@ static cudaError_t launch_g7(const Batch& b, const G7& g, int sm_count, cudaStre
     const size_t warps = ((size_t)b.n + 31) / 32;
     const char* we = getenv("CJ_G7_WARPS");   // experiments: warps per CTA (read per launch)
     const int force_w = we ? atoi(we) : 0;
-    const size_t rounds = std::max<size_t>(1, (warps + (size_t)sm_count * G7_MAX_WARPS - 1) / ((size_t)sm_count * G7_MAX_WARPS));
-    int w = (int)std::min<size_t>(G7_MAX_WARPS, std::max<size_t>(1, (warps + (size_t)sm_count * rounds - 1) / ((size_t)sm_count * rounds)));
-    if (force_w >= 1 && force_w <= G7_MAX_WARPS) w = force_w;
-    const int grid = (int)std::min<size_t>((warps + w - 1) / w, (size_t)sm_count * (size_t)std::max(1, G7_MAX_WARPS / w));
+    constexpr int MAXW = g7_max_warps(D);
+    const size_t rounds = std::max<size_t>(1, (warps + (size_t)sm_count * MAXW - 1) / ((size_t)sm_count * MAXW));
+    int w = (int)std::min<size_t>(MAXW, std::max<size_t>(1, (warps + (size_t)sm_count * rounds - 1) / ((size_t)sm_count * rounds)));
+    if (force_w >= 1 && force_w <= MAXW) w = force_w;
+    const int grid = (int)std::min<size_t>((warps + w - 1) / w, (size_t)sm_count * (size_t)std::max(1, MAXW / w));
     const size_t smem = (size_t)g7::cta_bytes(D, w);
     // The L1 share of the SM's 256 KB matters (re-reads of back-reference sectors hit it): ask for the smallest
     // shared-memory carve-out that holds the CTAs of one SM.

@@ -47,9 +47,12 @@ namespace g7 {
 constexpr int CODEC_SNAPPY = 0, CODEC_LZ4 = 2;   // = CJ_SNAPPY_RAW, CJ_LZ4_BLOCK (include/cramjam_cuda.h)
 constexpr uint32_t IN_G = 8;             // input ring granules per lane
 constexpr uint32_t INB = IN_G * 16;      // input ring bytes per lane
-constexpr uint32_t OUT_G = 4;            // granules of recent output per lane: the one being filled, two behind it, one ahead
+#ifndef CJ_G7_OUT_G
+#define CJ_G7_OUT_G 8
+#endif
+constexpr uint32_t OUT_G = CJ_G7_OUT_G;   // granules of recent output per lane: the one being filled, OUT_G - 2 behind it, one ahead
 constexpr uint32_t GROW = 512;           // bytes between consecutive granules of one lane (32 lanes x 16 bytes)
-constexpr uint32_t NEAR = 32;            // back-references up to this offset are read from the output ring at retire time
+constexpr uint32_t NEAR = (OUT_G - 2) * 16;   // back-references up to this offset are read from the output ring at retire time
 constexpr uint32_t MAXU = 1u << 30;
 constexpr uint32_t warp_bytes(int D) { return (IN_G + OUT_G + 2u * (uint32_t)D) * GROW; }   // + a staging pair per chunk in flight
 constexpr uint32_t cta_bytes(int D, int warps) { return warp_bytes(D) * (uint32_t)warps + 1024u; }   // + the 256-entry tag table
@@ -135,6 +138,9 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
     uint32_t tw0 = 0, tw1 = 0;       // the two ring words around ip, fetched one iteration ahead
     bool tw_ok = false;              // ... and whether they had arrived when they were fetched
     u4 acc = {0, 0, 0, 0};           // the output granule being filled: bytes [opr & ~15, opr)
+    u4 pend = acc;                   // a finished granule that starts a 32-byte sector waits here for its partner: the two leave with one 32-byte store
+    bool have_pend = false;
+    const uint32_t ph = (uint32_t)((uintptr_t)dst >> 4) & 1u;   // granule g of the output starts a 32-byte sector of memory iff g + ph is even
     // chunk in flight, per slot: M = bytes | (byte offset of its source window in the first granule) << 8;
     // G = shared-memory addresses of its two source granules (>> 4, 16 bits each)
     uint32_t M[D], G[D], IPH[D];
@@ -180,7 +186,14 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 lo.w = (acc.w & m3) | (y3 & ~m3);
                 const bool cross = (opr & 15u) + c >= 16u;   // the granule is complete: store it, go on with the upper half
                 const uint32_t ga = out_l + ((opr >> 4) & (OUT_G - 1)) * GROW, gb = out_l + (((opr >> 4) + 1u) & (OUT_G - 1)) * GROW;
-                env.stg128_if(dst + (opr & ~15u), lo, cross);
+                const bool odd = (((opr >> 4) + ph) & 1u) != 0;   // the finished granule is the second half of its sector
+                env.stg256_if(dst + (opr & ~15u) - 16, pend, lo, cross && odd && have_pend);
+                env.stg128_if(dst + (opr & ~15u), lo, cross && odd && !have_pend);   // no partner: only the first granule of a block that starts mid-sector
+                pend.x = cross ? lo.x : pend.x;
+                pend.y = cross ? lo.y : pend.y;
+                pend.z = cross ? lo.z : pend.z;
+                pend.w = cross ? lo.w : pend.w;
+                have_pend = cross ? !odd : have_pend;
                 acc.x = cross ? y4 : lo.x;
                 acc.y = cross ? y5 : lo.y;
                 acc.z = cross ? y6 : lo.z;
@@ -239,7 +252,7 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const uint32_t c16 = umin(rem, 16u);
                 const uint32_t k = opi & 3u;
                 const uint32_t fs = opi - sp;             // copy: output position of its source
-                const uint32_t F = opr & ~15u;            // output below F is in global memory
+                const uint32_t F = (opr & ~15u) - (have_pend ? 16u : 0u);   // output below F is in global memory
                 const bool isnear = sp <= NEAR;
                 IPH[u] = (is_lit && rem != 0) ? sp : ip;
                 // the source window starts k bytes before the source (those bytes are replaced by the accumulator's): its position
@@ -369,6 +382,7 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 else {
                     const uint32_t k = opr & 15u;   // the bytes of the unfinished granule
                     const uint32_t ga = out_l + ((opr >> 4) & (OUT_G - 1)) * GROW;
+                    env.stg128_if(dst + (opr & ~15u) - 16, pend, have_pend);   // a finished granule still waiting for its partner
                     for (uint32_t j = 0; j < k; j++) env.stg8(dst + (opr & ~15u) + j, env.lds8(ga + j));
                     env.finish_ok(opi);
                 }

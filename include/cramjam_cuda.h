@@ -115,8 +115,9 @@ const char* cj_status_string(int32_t status);    /* text used for the Python exc
 uint64_t cj_ctx_launch_count(const cj_ctx* ctx);
 /* Tuning knob, not part of the reference surface: which kernel family decodes LZ4 / Snappy block batches of at least
  * min_units units (smaller batches always take generation 2).  2 = one warp per block; 4 = one thread per
- * block with 8-byte chunks; 7 (default, min_units 32768) = one thread per block with 16-byte chunks and
- * granule rings.  Snappy raw and LZ4 block; results are identical on all of them. */
+ * block with 8-byte chunks; 7 (default) = one thread per block with 16-byte chunks and
+ * granule rings.  Snappy raw and LZ4 block (LZ4 batches need 1.5 x min_units); results are identical on all of
+ * them.  The default min_units is 16384. */
 int cj_ctx_set_decode_path(cj_ctx* ctx, int generation, long min_units);
 int cj_ctx_get_decode_path(const cj_ctx* ctx, int* generation, long* min_units);
 /* Diagnostics: how many units of the most recent thread-per-block batch were handed to the generation-2 kernel (waits for the stream). */

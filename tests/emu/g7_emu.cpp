@@ -82,6 +82,15 @@ struct HostEnv {
         memcpy(p, &v, 16);
         stored = o + 16;
     }
+    void stg256_if(uint8_t* p, u4 a, u4 c, bool pred) {
+        if (!pred) return;
+        const uint64_t o = (uint64_t)(p - dst_base);
+        if (((uintptr_t)p & 31u) != 0 || o + 32 > dst_cap) { fail(3); return; }
+        if (o != stored) fail(4);
+        memcpy(p, &a, 16);
+        memcpy(p + 16, &c, 16);
+        stored = o + 32;
+    }
     void stg8(uint8_t* p, uint32_t v) {
         const uint64_t o = (uint64_t)(p - dst_base);
         if (o >= dst_cap) { fail(5); return; }
