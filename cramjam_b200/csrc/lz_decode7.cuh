@@ -77,6 +77,18 @@ G7_HD uint32_t low_bits(uint32_t nbits) {   // mask of the low min(nbits, 32) bi
 #endif
 }
 G7_HD uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// m ? b : a for m in {0, 1}.  On the device two integer multiply-adds instead of a select: the kernel is bound by the ALU pipe
+// (selects, logic, shifts, compares: one warp instruction per two cycles), while the FMA pipe that executes IMAD idles.
+G7_HD uint32_t pick(uint32_t a, uint32_t b, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d, r;
+    asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(a), "r"(b));   // b - a
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(m), "r"(d), "r"(a));
+    return r;
+#else
+    return m ? b : a;
+#endif
+}
 G7_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
 
 // Snappy tag table: [6:0] compressed size of the element, [14:8] bytes it produces, [23:22] kind, [21:16] field,
@@ -164,17 +176,18 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
             // ---- retire: pick the six words the source window starts in, align them to the output phase, place them behind the
             //      bytes of the granule being filled ----
             {
-                const bool w1 = (d & 4u) != 0, w2 = (d & 8u) != 0;
-                const uint32_t u0 = w1 ? sa.y : sa.x, u1 = w1 ? sa.z : sa.y, u2 = w1 ? sa.w : sa.z, u3 = w1 ? sb.x : sa.w, u4_ = w1 ? sb.y : sb.x,
-                               u5 = w1 ? sb.z : sb.y, u6 = w1 ? sb.w : sb.z, u7 = sb.w;
-                const uint32_t t0 = w2 ? u2 : u0, t1 = w2 ? u3 : u1, t2 = w2 ? u4_ : u2, t3 = w2 ? u5 : u3, t4 = w2 ? u6 : u4_, t5 = w2 ? u7 : u5;
+                const uint32_t w1 = (d >> 2) & 1u, w2 = (d >> 3) & 1u;
+                const uint32_t u0 = pick(sa.x, sa.y, w1), u1 = pick(sa.y, sa.z, w1), u2 = pick(sa.z, sa.w, w1), u3 = pick(sa.w, sb.x, w1),
+                               u4_ = pick(sb.x, sb.y, w1), u5 = pick(sb.y, sb.z, w1), u6 = pick(sb.z, sb.w, w1), u7 = sb.w;
+                const uint32_t t0 = pick(u0, u2, w2), t1 = pick(u1, u3, w2), t2 = pick(u2, u4_, w2), t3 = pick(u3, u5, w2), t4 = pick(u4_, u6, w2),
+                               t5 = pick(u5, u7, w2);
                 const uint32_t sh = d * 8u;
                 const uint32_t x0 = funnel_r(t0, t1, sh), x1 = funnel_r(t1, t2, sh), x2 = funnel_r(t2, t3, sh), x3 = funnel_r(t3, t4, sh),
                                x4 = funnel_r(t4, t5, sh);
                 // x0..x4 hold the chunk from byte (opr & 3) of x0 on; word j of the 32-byte window takes x[j - wo], wo = word of opr
-                const bool o1 = (opr & 4u) != 0, o2 = (opr & 8u) != 0;
-                const uint32_t z0 = x0, z1 = o1 ? x0 : x1, z2 = o1 ? x1 : x2, z3 = o1 ? x2 : x3, z4 = o1 ? x3 : x4, z5 = x4;
-                const uint32_t y0 = z0, y1 = z1, y2 = o2 ? z0 : z2, y3 = o2 ? z1 : z3, y4 = o2 ? z2 : z4, y5 = o2 ? z3 : z5, y6 = z4, y7 = z5;
+                const uint32_t o1 = (opr >> 2) & 1u, o2 = (opr >> 3) & 1u;
+                const uint32_t z0 = x0, z1 = pick(x1, x0, o1), z2 = pick(x2, x1, o1), z3 = pick(x3, x2, o1), z4 = pick(x4, x3, o1), z5 = x4;
+                const uint32_t y0 = z0, y1 = z1, y2 = pick(z2, z0, o2), y3 = pick(z3, z1, o2), y4 = pick(z4, z2, o2), y5 = pick(z5, z3, o2), y6 = z4, y7 = z5;
                 // bytes below opr come from the accumulator
                 const int32_t ob = (int32_t)((opr & 15u) * 8u);
                 const uint32_t m0 = low_bits((uint32_t)ob), m1 = low_bits((uint32_t)imax(ob - 32, 0)), m2 = low_bits((uint32_t)imax(ob - 64, 0)),
@@ -189,15 +202,16 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const bool odd = (((opr >> 4) + ph) & 1u) != 0;   // the finished granule is the second half of its sector
                 env.stg256_if(dst + (opr & ~15u) - 16, pend, lo, cross && odd && have_pend);
                 env.stg128_if(dst + (opr & ~15u), lo, cross && odd && !have_pend);   // no partner: only the first granule of a block that starts mid-sector
-                pend.x = cross ? lo.x : pend.x;
-                pend.y = cross ? lo.y : pend.y;
-                pend.z = cross ? lo.z : pend.z;
-                pend.w = cross ? lo.w : pend.w;
+                const uint32_t cr = cross ? 1u : 0u;
+                pend.x = pick(pend.x, lo.x, cr);
+                pend.y = pick(pend.y, lo.y, cr);
+                pend.z = pick(pend.z, lo.z, cr);
+                pend.w = pick(pend.w, lo.w, cr);
                 have_pend = cross ? !odd : have_pend;
-                acc.x = cross ? y4 : lo.x;
-                acc.y = cross ? y5 : lo.y;
-                acc.z = cross ? y6 : lo.z;
-                acc.w = cross ? y7 : lo.w;
+                acc.x = pick(lo.x, y4, cross ? 1u : 0u);
+                acc.y = pick(lo.y, y5, cross ? 1u : 0u);
+                acc.z = pick(lo.z, y6, cross ? 1u : 0u);
+                acc.w = pick(lo.w, y7, cross ? 1u : 0u);
                 env.sts128(ga, lo);   // the output ring always holds the granule being filled as far as it is known
                 env.sts128_if(gb, acc, cross);
                 opr += c;
