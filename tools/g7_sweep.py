@@ -5,6 +5,12 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+if os.environ.get("EARLY_L2_FETCH"):   # experiment: cudaLimitMaxL2FetchGranularity set before anything else touches the device
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    v = ctypes.c_size_t()
+    print("cudaDeviceSetLimit ->", rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["EARLY_L2_FETCH"]))), flush=True)
+    print("cudaDeviceGetLimit ->", rt.cudaDeviceGetLimit(ctypes.byref(v), 5), v.value, flush=True)
 import torch
 from cramjam_b200 import _capi as capi
 
@@ -18,6 +24,7 @@ stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 c.set_stream(stream.cuda_stream)
 i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(dev)
+ORACLE = "--oracle" in sys.argv   # synthetic blocks encoded on the host by the oracle encoder (streams like the bench headline's Google-snappy ones)
 NEAR = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--near=")), 0)   # synthetic blocks whose offsets are folded below this distance
 def near_blocks(nb, cap, seed=1):
     rng = np.random.default_rng(seed)
@@ -48,12 +55,12 @@ def near_blocks(nb, cap, seed=1):
                 pos += ml
             i += 1
     return out.reshape(-1)
-if REAL or NEAR:
+if REAL or NEAR or ORACLE:
     import bz2
     import oracle as O
     cdir = os.path.join(ROOT, "tests", "golden", "corpus")
-    blobs = [np.frombuffer(bz2.decompress(open(os.path.join(cdir, f), "rb").read()), dtype=np.uint8) for f in sorted(os.listdir(cdir)) if f.endswith(".bz2")]
-    cdata = np.concatenate([b[: len(b) // U * U] for b in blobs]) if REAL else near_blocks(128, NEAR)
+    blobs = [] if not REAL else [np.frombuffer(bz2.decompress(open(os.path.join(cdir, f), "rb").read()), dtype=np.uint8) for f in sorted(os.listdir(cdir)) if f.endswith(".bz2")]
+    cdata = np.concatenate([b[: len(b) // U * U] for b in blobs]) if REAL else (near_blocks(128, NEAR) if NEAR else capi.synth_host(n, U))
     nb = len(cdata) // U
     rep = max(1, n // nb)
     n = nb * rep
@@ -69,7 +76,7 @@ for name in codecs:
     t_cl = torch.zeros(n, dtype=torch.int64, device=dev)
     t_st = torch.zeros(n, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
-    if REAL or NEAR:
+    if REAL or NEAR or ORACLE:
         comp = np.zeros(nb * slot + 64, dtype=np.uint8)
         so1, do1 = np.arange(nb, dtype=np.uint64) * np.uint64(U), np.arange(nb, dtype=np.uint64) * np.uint64(slot)
         lens = O.batch(O.LZ4_BLOCK if name == "lz4" else O.SNAPPY_RAW, 1, cdata, so1, np.full(nb, U, np.uint64), comp, do1, np.full(nb, slot, np.uint64), nthreads=os.cpu_count())[0]
@@ -100,7 +107,7 @@ for name in codecs:
         for _ in range(2):
             c.decompress_batch(codec, capi.DEVICE, n, t_cmp, t_co, t_cl, t_dst, t_uo, t_ul, t_dl, t_st)
         c.synchronize()
-        if REAL or NEAR:
+        if REAL or NEAR or ORACLE:
             got = t_dst[:n * U].view(rep, nb * U)
             ok = int((t_st != 0).sum()) == 0 and torch.equal(got[0], data) and torch.equal(got[rep - 1], data)
         else:
