@@ -20,7 +20,10 @@
 
 namespace cj {
 
-constexpr int ENC_WARPS = 4;
+#ifndef CJ_ENC_WARPS
+#define CJ_ENC_WARPS 14   // warps per CTA: 2 CTAs x 14 warps x 8 KiB tables fill an SM (28 warps); 4-warp CTAs stop at 6 CTAs = 24 warps (1 KB of shared memory is reserved per CTA)
+#endif
+constexpr int ENC_WARPS = CJ_ENC_WARPS;
 
 struct EncOut {
     uint8_t* dst;

@@ -109,9 +109,7 @@ struct BackBits {
         const uint32_t sft = (uint32_t)(lo - wbit);
         const uint32_t w0 = (uint32_t)win, w1 = (uint32_t)(win >> 32);
         const uint32_t v = (sft & 32) ? (w1 >> (sft & 31)) : __funnelshift_r(w0, w1, sft);
-        uint32_t r;
-        asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(nb));
-        return r;
+        return v & __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)nb);   // low nb bits (nb <= 32; the clamped funnel shift builds the mask in one instruction, bfe is emulated)
     }
     __device__ __forceinline__ uint32_t read(int nb) {
         const uint32_t v = peek(nb);
@@ -184,10 +182,9 @@ __device__ int fse_read_desc_lane0(uint32_t* tab, int* al_out, const uint8_t* p,
 __constant__ int16_t ZS_LL_DEFAULT[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
 __constant__ int16_t ZS_ML_DEFAULT[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
 __constant__ int16_t ZS_OF_DEFAULT[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
-__constant__ uint32_t ZS_LL_BASE[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-__constant__ uint8_t ZS_LL_BITS[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-__constant__ uint32_t ZS_ML_BASE[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-__constant__ uint8_t ZS_ML_BITS[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+// baseline value | number of extra bits << 24, per literal-length / match-length code (RFC 8878 3.1.1.3.2.1.1): one constant load per code
+__constant__ uint32_t ZS_LL_PK[36] = {0x0, 0x1, 0x2, 0x3, 0x4, 0x5, 0x6, 0x7, 0x8, 0x9, 0xa, 0xb, 0xc, 0xd, 0xe, 0xf, 0x1000010, 0x1000012, 0x1000014, 0x1000016, 0x2000018, 0x200001c, 0x3000020, 0x3000028, 0x4000030, 0x6000040, 0x7000080, 0x8000100, 0x9000200, 0xa000400, 0xb000800, 0xc001000, 0xd002000, 0xe004000, 0xf008000, 0x10010000};
+__constant__ uint32_t ZS_ML_PK[53] = {0x3, 0x4, 0x5, 0x6, 0x7, 0x8, 0x9, 0xa, 0xb, 0xc, 0xd, 0xe, 0xf, 0x10, 0x11, 0x12, 0x13, 0x14, 0x15, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x1b, 0x1c, 0x1d, 0x1e, 0x1f, 0x20, 0x21, 0x22, 0x1000023, 0x1000025, 0x1000027, 0x1000029, 0x200002b, 0x200002f, 0x3000033, 0x300003b, 0x4000043, 0x4000053, 0x5000063, 0x7000083, 0x8000103, 0x9000203, 0xa000403, 0xb000803, 0xc001003, 0xd002003, 0xe004003, 0xf008003, 0x10010003};
 
 // Sets up one sequence table according to its mode.  Returns bytes consumed or -1.  Warp-uniform result.
 __device__ int seq_table(FseTab& t, int mode, const uint8_t* p, uint32_t n, const int16_t* def, int def_n, int def_al, int max_al, int max_sym,
@@ -438,10 +435,11 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
                 const uint32_t el = z.ll.t[sl], eo = z.of.t[so], em = z.ml.t[sm];
                 const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
                 const uint32_t ovx = b.read((int)oc);                        // offset extra bits (<= 31)
-                const uint32_t mlb = ZS_ML_BITS[mc], llb = ZS_LL_BITS[lc];
+                const uint32_t mpk = ZS_ML_PK[mc], lpk = ZS_LL_PK[lc];
+                const uint32_t mlb = mpk >> 24, llb = lpk >> 24;
                 const uint32_t t = b.read((int)(mlb + llb));                 // match-length then literal-length extra bits (<= 32)
-                const uint32_t mlen = ZS_ML_BASE[mc] + (t >> llb);
-                const uint32_t llen = ZS_LL_BASE[lc] + (t & ((1u << llb) - 1));
+                const uint32_t mlen = (mpk & 0xFFFFFFu) + (t >> llb);
+                const uint32_t llen = (lpk & 0xFFFFFFu) + (t & ((1u << llb) - 1));
                 bool bad = false;
                 uint32_t off;
                 if (oc >= 2) {
