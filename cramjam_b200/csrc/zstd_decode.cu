@@ -19,28 +19,37 @@
 namespace cj {
 
 #ifndef CJ_ZS_WARPS
-#define CJ_ZS_WARPS 3
+#define CJ_ZS_WARPS 10
 #endif
 #ifndef CJ_ZS_CTAS
-#define CJ_ZS_CTAS 5
+#define CJ_ZS_CTAS 2
 #endif
-constexpr int ZS_WARPS = CJ_ZS_WARPS;   // 3 warps x 14.5 KiB: five CTAs (15 warps) fit an SM, four 4-warp CTAs would not
+constexpr int ZS_WARPS = CJ_ZS_WARPS;   // 10 warps x 11.1 KiB: two CTAs (20 warps) fit an SM
 constexpr uint32_t ZS_BLOCK_MAX = 128 * 1024;
 constexpr size_t ZS_LIT_STRIDE = ZS_BLOCK_MAX + 64;  // per-warp literal buffer in global scratch
 
-// per-warp shared memory layout
-constexpr int ZS_OFF_HUF = ORING;                       // 2048 x u16
-constexpr int ZS_OFF_LL = ZS_OFF_HUF + 2048 * 2;        // 512 x u32
-constexpr int ZS_OFF_OF = ZS_OFF_LL + 512 * 4;          // 256 x u32
-constexpr int ZS_OFF_ML = ZS_OFF_OF + 256 * 4;          // 512 x u32
-constexpr int ZS_OFF_TMP = ZS_OFF_ML + 512 * 4;         // 256 x i16 frequencies + 256 x u16 next-state counters + 260 weights + 64 x u32 weight-FSE table
-constexpr int ZS_SMEM_WARP = ZS_OFF_TMP + 512 + 512 + 272 + 256;
+// per-warp shared memory layout.  The Huffman table (needed while a block's literals are decoded) and the three FSE tables (needed
+// while its sequences are decoded) share one region: the kernel is bound by the latency of its serial bit chains, so resident warps
+// are what it needs (15 -> 20 per SM).  What a later block may ask to reuse (treeless literals, Repeat_Mode tables) is kept as its
+// description — Huffman weights, normalized counts — and rebuilt when the region held the other kind in between.
+constexpr int ZS_OFF_U = ORING;                         // union: 2048 x u16 Huffman table | LL 512 + OF 256 + ML 512 x u32 FSE tables
+constexpr int ZS_OFF_HUF = ZS_OFF_U;
+constexpr int ZS_OFF_LL = ZS_OFF_U;
+constexpr int ZS_OFF_OF = ZS_OFF_LL + 512 * 4;
+constexpr int ZS_OFF_ML = ZS_OFF_OF + 256 * 4;
+constexpr int ZS_OFF_TMP = ZS_OFF_ML + 512 * 4;         // 256 x i16 frequencies + 256 x u16 next-state counters + 272 weights + 64 x u32 weight-FSE table
+constexpr int ZS_OFF_SAVE = ZS_OFF_TMP + 512 + 512 + 272 + 256;   // saved descriptions: 256 Huffman weights | LL 36 + OF 32 + ML 53 (+7 pad) x i16 counts
+constexpr int ZS_SMEM_WARP = ZS_OFF_SAVE + 256 + (36 + 32 + 60) * 2;
 static_assert(ZS_SMEM_WARP % 16 == 0, "per-warp shared memory must stay 16-byte aligned");
 
 struct FseTab {
     uint32_t* t;  // entry = sym | nbits << 8 | base << 16
     int al;
-    bool ok;
+    bool ok;      // a table has been set up in this frame (Repeat_Mode may refer to it)
+    bool live;    // ... and it is in shared memory right now (the Huffman table has not been built over it since)
+    int kind;     // how it was set up: 0 predefined, 1 RLE (sym), 2 described (counts saved)
+    int sym, nsym;
+    int16_t* saved;   // normalized counts of a described table
 };
 
 __device__ __forceinline__ int hibit(uint32_t v) { return 31 - __clz(v); }
@@ -146,7 +155,7 @@ __device__ bool fse_build_lane0(uint32_t* tab, const int16_t* freq, uint16_t* ne
 }
 
 // Reads an FSE table description at p (lane 0); returns bytes consumed or -1.
-__device__ int fse_read_desc_lane0(uint32_t* tab, int* al_out, const uint8_t* p, uint32_t n, int max_al, int max_sym, int16_t* freq, uint16_t* next) {
+__device__ int fse_read_desc_lane0(uint32_t* tab, int* al_out, const uint8_t* p, uint32_t n, int max_al, int max_sym, int16_t* freq, uint16_t* next, int* nsym_out = nullptr) {
     if (n == 0) return -1;
     FwdBits b{p, n, 0};
     const int al = 5 + (int)b.read(4);
@@ -176,6 +185,7 @@ __device__ int fse_read_desc_lane0(uint32_t* tab, int* al_out, const uint8_t* p,
     if (used > n) return -1;
     if (!fse_build_lane0(tab, freq, next, s, al)) return -1;
     *al_out = al;
+    if (nsym_out) *nsym_out = s;
     return (int)used;
 }
 
@@ -189,22 +199,43 @@ __constant__ uint32_t ZS_ML_PK[53] = {0x3, 0x4, 0x5, 0x6, 0x7, 0x8, 0x9, 0xa, 0x
 // Sets up one sequence table according to its mode.  Returns bytes consumed or -1.  Warp-uniform result.
 __device__ int seq_table(FseTab& t, int mode, const uint8_t* p, uint32_t n, const int16_t* def, int def_n, int def_al, int max_al, int max_sym,
                          int16_t* freq, uint16_t* next, int lane) {
-    int consumed = -1, al = t.al;
-    if (mode == 3) return t.ok ? 0 : -1;
+    int consumed = -1, al = t.al, sym = t.sym, nsym = t.nsym;
+    if (mode == 3) {   // Repeat_Mode: the previous table — still there, or rebuilt from what was saved of it
+        if (!t.ok) return -1;
+        if (t.live) return 0;
+        int good = 0;
+        if (lane == 0) {
+            if (t.kind == 1) { t.t[0] = (uint32_t)t.sym; good = 1; }
+            else {
+                const int16_t* from = t.kind == 0 ? def : t.saved;
+                const int cnt = t.kind == 0 ? def_n : t.nsym;
+                for (int i = 0; i < cnt; i++) freq[i] = from[i];
+                good = fse_build_lane0(t.t, freq, next, cnt, t.al) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+        good = __shfl_sync(FULL, good, 0);
+        if (!good) return -1;
+        t.live = true;
+        return 0;
+    }
     if (lane == 0) {
         if (mode == 0) {
             for (int i = 0; i < def_n; i++) freq[i] = def[i];
             if (fse_build_lane0(t.t, freq, next, def_n, def_al)) { consumed = 0; al = def_al; }
         } else if (mode == 1) {
-            if (n >= 1 && __ldg(p) <= max_sym) { t.t[0] = __ldg(p); consumed = 1; al = 0; }
+            if (n >= 1 && __ldg(p) <= max_sym) { sym = __ldg(p); t.t[0] = (uint32_t)sym; consumed = 1; al = 0; }
         } else {
-            consumed = fse_read_desc_lane0(t.t, &al, p, n, max_al, max_sym, freq, next);
+            consumed = fse_read_desc_lane0(t.t, &al, p, n, max_al, max_sym, freq, next, &nsym);
+            if (consumed >= 0) for (int i = 0; i < nsym; i++) t.saved[i] = freq[i];   // freq[] still holds the counts as read
         }
     }
     __syncwarp();
     consumed = __shfl_sync(FULL, consumed, 0);
     al = __shfl_sync(FULL, al, 0);
-    if (consumed >= 0) { t.al = al; t.ok = true; }
+    sym = __shfl_sync(FULL, sym, 0);
+    nsym = __shfl_sync(FULL, nsym, 0);
+    if (consumed >= 0) { t.al = al; t.ok = true; t.live = true; t.kind = mode; t.sym = sym; t.nsym = nsym; }
     return consumed;
 }
 
@@ -237,7 +268,7 @@ __device__ int huf_build_lane0(uint16_t* huf, uint8_t* w, int nw) {
 }
 
 // Reads the Huffman tree description (lane 0).  Returns bytes consumed or -1; *max_bits set.
-__device__ int huf_read_desc_lane0(uint16_t* huf, int* max_bits, const uint8_t* p, uint32_t n, uint32_t* fse_scratch, int16_t* freq, uint16_t* next, uint8_t* w) {
+__device__ int huf_read_desc_lane0(uint16_t* huf, int* max_bits, const uint8_t* p, uint32_t n, uint32_t* fse_scratch, int16_t* freq, uint16_t* next, uint8_t* w, uint8_t* w_saved, int* nw_saved) {
     if (n == 0) return -1;
     int nw = 0;
     const int hb = __ldg(p);
@@ -274,6 +305,8 @@ __device__ int huf_read_desc_lane0(uint16_t* huf, int* max_bits, const uint8_t* 
         }
         used = 1 + (uint32_t)hb;
     }
+    for (int i = 0; i < nw; i++) w_saved[i] = w[i];   // the explicit weights: what a treeless block rebuilds the table from
+    *nw_saved = nw;
     const int mb = huf_build_lane0(huf, w, nw);
     if (mb < 0) return -1;
     *max_bits = mb;
@@ -296,7 +329,10 @@ __device__ bool huf_decode_stream(const uint16_t* huf, int max_bits, const uint8
 struct ZState {
     uint16_t* huf;
     int huf_bits;
-    bool huf_ok;
+    bool huf_ok;     // a Huffman table has been described in this frame (treeless literals may refer to it)
+    bool huf_live;   // ... and it is in shared memory right now (no FSE table has been built over it since)
+    uint8_t* huf_w;  // its explicit weights, saved
+    int huf_nw;
     FseTab ll, of, ml;
     uint32_t rep0, rep1, rep2;
     int16_t* freq;
@@ -350,18 +386,35 @@ __device__ int zs_literals(ZState& z, const uint8_t* p, uint32_t n, const uint8_
     const uint8_t* q = p + hdr;
     uint32_t left = comp;
     if (type == 2) {
-        int c = -1, mb = 0;
-        if (lane == 0) c = huf_read_desc_lane0(z.huf, &mb, q, left, z.wfse, z.freq, z.next, z.w);
+        int c = -1, mb = 0, nw = 0;
+        z.ll.live = z.of.live = z.ml.live = false;   // the Huffman table is built over the FSE tables
+        z.huf_live = false;
+        if (lane == 0) c = huf_read_desc_lane0(z.huf, &mb, q, left, z.wfse, z.freq, z.next, z.w, z.huf_w, &nw);
         __syncwarp();
         c = __shfl_sync(FULL, c, 0);
         mb = __shfl_sync(FULL, mb, 0);
-        if (c < 0) return -CJ_ST_CORRUPT;
+        nw = __shfl_sync(FULL, nw, 0);
+        if (c < 0) { z.huf_ok = false; return -CJ_ST_CORRUPT; }
         z.huf_bits = mb;
+        z.huf_nw = nw;
         z.huf_ok = true;
+        z.huf_live = true;
         q += c;
         left -= (uint32_t)c;
     } else if (!z.huf_ok) {
         return -CJ_ST_CORRUPT;  // treeless without a previous table
+    } else if (!z.huf_live) {   // treeless: the previous table, rebuilt from its saved weights
+        int mb = -1;
+        z.ll.live = z.of.live = z.ml.live = false;
+        if (lane == 0) {
+            for (int i = 0; i < z.huf_nw; i++) z.w[i] = z.huf_w[i];
+            mb = huf_build_lane0(z.huf, z.w, z.huf_nw);
+        }
+        __syncwarp();
+        mb = __shfl_sync(FULL, mb, 0);
+        if (mb < 0) return -CJ_ST_CORRUPT;
+        z.huf_bits = mb;
+        z.huf_live = true;
     }
     bool ok = true;
     if (streams == 1) {
@@ -412,6 +465,7 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
         const uint32_t modes = __ldg(p);
         if (modes & 3) return CJ_ST_CORRUPT;
         p++; n--;
+        z.huf_live = false;   // the FSE tables are built over the Huffman table (its literals are decoded already)
         c = seq_table(z.ll, (modes >> 6) & 3, p, n, ZS_LL_DEFAULT, 36, 6, 9, 35, z.freq, z.next, lane);
         if (c < 0) return CJ_ST_CORRUPT;
         p += c; n -= (uint32_t)c;
@@ -548,6 +602,10 @@ __device__ int32_t zstd_decode_stream(const uint8_t* __restrict__ src, uint32_t 
     z.next = reinterpret_cast<uint16_t*>(smem_warp + ZS_OFF_TMP + 512);
     z.w = smem_warp + ZS_OFF_TMP + 1024;
     z.wfse = reinterpret_cast<uint32_t*>(smem_warp + ZS_OFF_TMP + 1024 + 272);
+    z.huf_w = smem_warp + ZS_OFF_SAVE;
+    z.ll.saved = reinterpret_cast<int16_t*>(smem_warp + ZS_OFF_SAVE + 256);
+    z.of.saved = z.ll.saved + 36;
+    z.ml.saved = z.of.saved + 32;
     z.lit = lit_buf;
     uint32_t ip = 0;
     int32_t st = CJ_OK;
@@ -594,8 +652,13 @@ __device__ int32_t zstd_decode_stream(const uint8_t* __restrict__ src, uint32_t 
         const uint32_t bmax = window < ZS_BLOCK_MAX ? (uint32_t)window : ZS_BLOCK_MAX;
         const uint32_t frame_start = out.op;
         out.base = frame_start;
-        z.huf_ok = false;
+        z.huf_ok = z.huf_live = false;
+        z.huf_nw = 0;
         z.ll.ok = z.of.ok = z.ml.ok = false;
+        z.ll.live = z.of.live = z.ml.live = false;
+        z.ll.kind = z.of.kind = z.ml.kind = 0;
+        z.ll.sym = z.of.sym = z.ml.sym = 0;
+        z.ll.nsym = z.of.nsym = z.ml.nsym = 0;
         z.ll.al = z.of.al = z.ml.al = 0;
         z.rep0 = 1; z.rep1 = 4; z.rep2 = 8;
         // ---- blocks ----
@@ -668,7 +731,7 @@ __global__ void __launch_bounds__(ZS_WARPS * 32) zstd_decode_kernel(Batch b, uns
 }
 
 int zstd_grid(int sm_count, uint32_t n) {
-    int grid = sm_count * CJ_ZS_CTAS;  // CTAs x warps x 14.5 KiB of shared memory per SM
+    int grid = sm_count * CJ_ZS_CTAS;  // CTAs x warps x 11.1 KiB of shared memory per SM
     const int need = (int)((n + ZS_WARPS - 1) / ZS_WARPS);
     if (grid > need) grid = need;
     return grid < 1 ? 1 : grid;
