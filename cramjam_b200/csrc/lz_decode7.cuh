@@ -153,11 +153,11 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
     u4 pend = acc;                   // a finished granule that starts a 32-byte sector waits here for its partner: the two leave with one 32-byte store
     bool have_pend = false;
     const uint32_t ph = (uint32_t)((uintptr_t)dst >> 4) & 1u;   // granule g of the output starts a 32-byte sector of memory iff g + ph is even
-    // chunk in flight, per slot: M = bytes | (byte offset of its source window in the first granule) << 8;
-    // G = shared-memory addresses of its two source granules (>> 4, 16 bits each)
-    uint32_t M[D], G[D], IPH[D];
+    // chunk in flight, per slot: M = bytes, DD = byte offset of its source window in the first of its two source granules,
+    // GA / GB = shared-memory addresses of those granules (registers are not the scarce resource here, ALU instructions are)
+    uint32_t M[D], DD[D], GA[D], GB[D], IPH[D];
 #pragma unroll
-    for (int u = 0; u < D; u++) { M[u] = 0; G[u] = (out_l >> 4) | ((out_l >> 4) << 16); IPH[u] = 0; }
+    for (int u = 0; u < D; u++) { M[u] = 0; DD[u] = 0; GA[u] = out_l; GB[u] = out_l; IPH[u] = 0; }
 
     while (env.any(st != IDLE)) {
 #pragma unroll
@@ -167,9 +167,8 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
             if (u == 0) lim = lnext;   // the pair requested one pass ago has arrived
             // ---- loads first: the two source granules of the chunk issued one pass ago, and the table entry of the tag fetched one
             //      iteration ago ----
-            const uint32_t m = M[u];
-            const uint32_t c = m & 31u, d = m >> 8;
-            const u4 sa = env.lds128((G[u] & 0xFFFFu) << 4), sb = env.lds128((G[u] >> 16) << 4);
+            const uint32_t c = M[u], d = DD[u];
+            const u4 sa = env.lds128(GA[u]), sb = env.lds128(GB[u]);
             const uint32_t t = funnel_r(tw0, tw1, ip * 8u);   // the funnel shift takes its amount mod 32
             uint32_t ent = 0;
             if (CODEC == CODEC_SNAPPY) ent = env.lds32(lut + 4u * (t & 255u));
@@ -288,8 +287,10 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const uint32_t gi = sk >> 4;
                 const bool ring = is_lit || isnear;
                 const uint32_t a0 = ring ? rbase + (gi & rmask) * GROW : s0, a1 = ring ? rbase + ((gi + 1u) & rmask) * GROW : s0 + GROW;
-                G[u] = (a0 >> 4) | ((a1 >> 4) << 16);
-                M[u] = cn | (dd << 8);
+                GA[u] = a0;
+                GB[u] = a1;
+                M[u] = cn;
+                DD[u] = dd;
                 sp = is_lit ? sp + cn : ((cn == sp && sp < 16u) ? sp + sp : sp);
                 opi += cn;
                 rem -= cn;
@@ -390,7 +391,7 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
         if (st == DRAIN) {
             bool empty = true;
 #pragma unroll
-            for (int u = 0; u < D; u++) empty = empty && (M[u] & 31u) == 0;
+            for (int u = 0; u < D; u++) empty = empty && M[u] == 0;
             if (empty) {
                 if (CODEC == CODEC_SNAPPY && opi != ulen) env.redo();
                 else {
