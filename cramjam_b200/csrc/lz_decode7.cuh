@@ -247,8 +247,9 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const uint32_t mlx = mln == 15u ? 1u : 0u;
                 const uint32_t mtot = mln + 4 + (mlx ? xb : 0u), madv = (o8 >> 3) + 2 + mlx;
                 const bool longrun = lit0 ? (llx && b1 == 255u) : (mlx && xb == 255u);
-                const bool tailz = !lz_phase && ((uint64_t)opi + ll_tot + 12 > ulen || (uint64_t)q + ll_tot + 8 > n);
-                const bool mbad = !lit0 && (offv - 1u >= opi || (uint64_t)opi + mtot + 5 > ulen || ip + madv > n);
+                // 32-bit sums cannot wrap: positions are at most MAXU = 2^30, the lengths of this path at most 15 + 255 + 4
+                const bool tailz = !lz_phase && (opi + ll_tot + 12u > ulen || q + ll_tot + 8u > n);
+                const bool mbad = !lit0 && (offv - 1u >= opi || opi + mtot + 5u > ulen || ip + madv > n);
                 const bool bad = longrun || tailz || mbad;
                 const bool take = fast && !bad;
                 slow = (fast && bad) || (need && atend && !lz_last);

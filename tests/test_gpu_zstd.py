@@ -169,3 +169,53 @@ def test_zstd_encode_levels_and_huffman_literals():
         assert sizes[3][i] <= sizes[1][i], (i, sizes[3][i], sizes[1][i])
     assert sizes[3][4] < sizes[1][4] * 0.9, (sizes[3][4], sizes[1][4])   # the synthetic corpus: literals are ~45 % of the frame
     assert sum(sizes[3]) < sum(sizes[1]) * 0.97
+
+
+def _block_modes(f):
+    """(literal section types, sequence table modes) of the compressed blocks of one zstd frame — header walk only."""
+    p = 4
+    fhd = f[p]; p += 1
+    single, fcs, did = (fhd >> 5) & 1, fhd >> 6, fhd & 3
+    p += (0 if single else 1) + [0, 1, 2, 4][did] + [1 if single else 0, 2, 4, 8][fcs]
+    lit, seq = [], []
+    while True:
+        h = f[p] | f[p + 1] << 8 | f[p + 2] << 16; p += 3
+        last, bt, bs = h & 1, (h >> 1) & 3, h >> 3
+        if bt == 2:
+            b0 = f[p]; lt, sf = b0 & 3, (b0 >> 2) & 3
+            lit.append(lt)
+            if lt < 2:
+                hdr, regen = (1, b0 >> 3) if sf in (0, 2) else ((2, (b0 >> 4) | (f[p + 1] << 4)) if sf == 1 else (3, (b0 >> 4) | (f[p + 1] << 4) | (f[p + 2] << 12)))
+                q = p + hdr + (regen if lt == 0 else 1)
+            else:
+                v = int.from_bytes(f[p:p + 5], "little")
+                hdr, comp = (3, (v >> 14) & 0x3ff) if sf in (0, 1) else ((4, (v >> 18) & 0x3fff) if sf == 2 else (5, (v >> 22) & 0x3ffff))
+                q = p + hdr + comp
+            n0 = f[q]
+            if n0:
+                m = f[q + (1 if n0 < 128 else (2 if n0 < 255 else 3))]
+                seq.append(((m >> 6) & 3, (m >> 4) & 3, (m >> 2) & 3))
+        p += bs if bt != 1 else 1
+        if last:
+            return lit, seq
+
+
+@pytest.mark.skipif(not S.have_zstd, reason="libzstd.so.1 not present")
+def test_treeless_literals_and_repeat_mode_tables():
+    """Multi-block frames whose later blocks reuse the previous Huffman table (treeless literals) and the previous FSE tables
+    (Repeat_Mode): the decode kernel keeps both kinds of table in ONE shared-memory region and rebuilds what a block reuses
+    from its saved description (zstd_decode.cu), so these modes must be in the test set, not just happen to be."""
+    datas = [corpus.text(1 << 20, 5), corpus.lz_model(1 << 20, 6), capi.synth_host(16, 65536, seed=0xC0FFEE).tobytes()]
+    units, want, treeless, repeats = [], [], 0, 0
+    for d in datas:
+        for lvl in (1, 3, 9, 19):
+            f = S.zstd_compress(d, level=lvl)
+            lit, seq = _block_modes(f)
+            treeless += lit.count(3)
+            repeats += sum(s.count(3) for s in seq)
+            units.append(f)
+            want.append(d)
+    assert treeless >= 10 and repeats >= 10, (treeless, repeats)
+    outs, st = ctx().run_host_units(capi.ZSTD, False, units, [len(d) for d in want])
+    assert (st == 0).all(), [(i, int(s)) for i, s in enumerate(st) if s]
+    assert outs == want
