@@ -18,7 +18,7 @@
 
 namespace cj {
 
-constexpr int ZE_WARPS = 4;
+constexpr int ZE_WARPS = 11;   // two CTAs of 11 warps (22 warps x 9.5 KiB) fit an SM; five 4-warp CTAs hold 20 (1 KB of shared memory is reserved per CTA)
 constexpr uint32_t ZE_BLOCK = 128 * 1024;
 constexpr uint32_t ZE_MAXSEQ = ZE_BLOCK / 4 + 8;                       // every match is >= 4 bytes
 constexpr size_t ZE_HUF_TMP = 256 + 4 * ((size_t)ZE_BLOCK / 4 * 3 / 2 + 64);          // tree description + four streams at their worst case (11 bits per symbol)
@@ -351,7 +351,7 @@ static cudaError_t upload_tables() {
 }
 
 int zstd_enc_grid(int sm_count, uint32_t n) {
-    int grid = sm_count * 5;  // 9.5 KiB of shared memory per warp (match table + Huffman histogram / codes): 20 warps per SM
+    int grid = sm_count * 2;  // 9.5 KiB of shared memory per warp (match table + Huffman histogram / codes): 22 warps per SM
     const int need = (int)((n + ZE_WARPS - 1) / ZE_WARPS);
     if (grid > need) grid = need;
     return grid < 1 ? 1 : grid;
@@ -364,13 +364,14 @@ cudaError_t launch_zstd_encode(const Batch& b, unsigned* counter, uint8_t* scrat
     // libzstd's levels trade speed for ratio; here: levels 1-2 and the negative ("fast") levels store literals raw, every
     // other level (0 = the library default 3 included) adds the Huffman literal stage
     const int huffman = (level == 1 || level == 2 || level < 0) ? 0 : 1;
-    static bool ready = false;
+    static cj_per_device_flag ready_flag;   // constant tables and the attribute belong to the device the call is made on
+    int& ready = ready_flag.here();
     if (!ready) {
         cudaError_t e = upload_tables();
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(zstd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        ready = true;
+        ready = 1;
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
