@@ -149,7 +149,7 @@ static cudaError_t launch_g7(const Batch& b, const G7& g, int sm_count, cudaStre
 
 cudaError_t launch_lz_decode7(int codec, const Batch& b, LzScratch& sc, int sm_count, cudaStream_t stream) {
     const char* de = getenv("CJ_G7_D");   // experiments: chunks in flight per lane (read per launch)
-    const int depth = de ? atoi(de) : (codec == CJ_LZ4_BLOCK ? 4 : 3);   // measured best at 65 536 x 64 KiB: Snappy 3 (6.6 ms; 2: 6.9, 4: 7.1), LZ4 4 (8.6 ms; 2: 9.0, 3: 8.8)
+    const int depth = de ? atoi(de) : 3;   // measured at 65 536 x 64 KiB: Snappy 6.5 ms at 3 (2: 6.7, 4: 7.0) on GPU-made streams, 8.0 / 8.0 / 8.4 on host-made ones; LZ4 8.2 ms at 3 on host-made streams (2: 8.4, 4: 8.6), 8.1 vs 8.0 at 4 on GPU-made ones
     const size_t n = b.n;
     if (sc.ensure_fixed((n + 8) * 4 + 64) != 0) return cudaErrorMemoryAllocation;
     G7 g;
