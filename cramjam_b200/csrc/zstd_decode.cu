@@ -125,6 +125,23 @@ struct BackBits {
         pos -= nb;
         return v;
     }
+    // The next `total` bits (total <= 56 <= pos) as the top of a 64-bit value {hi, lo}: one window check for all the fields of a
+    // sequence, which are then peeled off the top with take().  Consumes the bits.
+    __device__ __forceinline__ void top(uint32_t total, uint32_t& hi, uint32_t& lo) {
+        if ((int32_t)(pos - (int32_t)total) < wbit) refill();   // afterwards the window holds at least the 57 bits below pos
+        const uint32_t s = 64u - (uint32_t)(pos - wbit);       // window bit 63 - s is stream bit pos - 1; 0 <= s <= 63
+        const uint32_t w0 = (uint32_t)win, w1 = (uint32_t)(win >> 32);
+        const bool big = (s & 32u) != 0;
+        hi = big ? (w0 << (s & 31u)) : __funnelshift_l(w0, w1, s);
+        lo = big ? 0u : (w0 << (s & 31u));
+        pos -= (int32_t)total;
+    }
+    static __device__ __forceinline__ uint32_t take(uint32_t& hi, uint32_t& lo, uint32_t nb) {   // nb <= 31
+        const uint32_t v = __funnelshift_rc(hi, 0u, 32u - nb);   // hi >> (32 - nb), 0 for nb == 0
+        hi = __funnelshift_l(lo, hi, nb);
+        lo <<= nb;
+        return v;
+    }
 };
 
 // ---- FSE ----
@@ -488,12 +505,27 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
                 // table symbols are range-checked when the tables are built, so codes index the constant tables safely
                 const uint32_t el = z.ll.t[sl], eo = z.of.t[so], em = z.ml.t[sm];
                 const uint32_t lc = el & 0xff, oc = eo & 0xff, mc = em & 0xff;
-                const uint32_t ovx = b.read((int)oc);                        // offset extra bits (<= 31)
                 const uint32_t mpk = ZS_ML_PK[mc], lpk = ZS_LL_PK[lc];
                 const uint32_t mlb = mpk >> 24, llb = lpk >> 24;
-                const uint32_t t = b.read((int)(mlb + llb));                 // match-length then literal-length extra bits (<= 32)
-                const uint32_t mlen = (mpk & 0xFFFFFFu) + (t >> llb);
-                const uint32_t llen = (lpk & 0xFFFFFFu) + (t & ((1u << llb) - 1));
+                const bool more = i0 + k + 1 < nseq;   // state updates follow: LL, ML, OF bits in that order (<= 9 + 9 + 8)
+                const uint32_t nl = (el >> 8) & 0xff, nm = (em >> 8) & 0xff, no = (eo >> 8) & 0xff;
+                const uint32_t total = oc + mlb + llb + (more ? nl + nm + no : 0u);
+                uint32_t ovx, mlx, llx;
+                const bool one = total <= 56u && (int32_t)total <= b.pos;   // all fields of the sequence from one window (nearly always)
+                uint32_t fh = 0, fl = 0;
+                if (one) {
+                    b.top(total, fh, fl);
+                    ovx = BackBits::take(fh, fl, oc);        // offset extra bits (<= 31)
+                    mlx = BackBits::take(fh, fl, mlb);       // match-length extra bits (<= 16)
+                    llx = BackBits::take(fh, fl, llb);       // literal-length extra bits (<= 16)
+                } else {
+                    ovx = b.read((int)oc);
+                    const uint32_t t = b.read((int)(mlb + llb));
+                    mlx = t >> llb;
+                    llx = t & ((1u << llb) - 1);
+                }
+                const uint32_t mlen = (mpk & 0xFFFFFFu) + mlx;
+                const uint32_t llen = (lpk & 0xFFFFFFu) + llx;
                 bool bad = false;
                 uint32_t off;
                 if (oc >= 2) {
@@ -512,12 +544,17 @@ __device__ int32_t zs_block(ZState& z, const uint8_t* p, uint32_t n, OutRing& ou
                         off = v;
                     }
                 }
-                if (i0 + k + 1 < nseq) {  // state updates: LL, ML, OF bits in that order (<= 9 + 9 + 8)
-                    const uint32_t nl = (el >> 8) & 0xff, nm = (em >> 8) & 0xff, no = (eo >> 8) & 0xff;
-                    const uint32_t u = b.read((int)(nl + nm + no));
-                    sl = (el >> 16) + (u >> (nm + no));
-                    sm = (em >> 16) + ((u >> no) & ((1u << nm) - 1));
-                    so = (eo >> 16) + (u & ((1u << no) - 1));
+                if (more) {
+                    if (one) {
+                        sl = (el >> 16) + BackBits::take(fh, fl, nl);
+                        sm = (em >> 16) + BackBits::take(fh, fl, nm);
+                        so = (eo >> 16) + BackBits::take(fh, fl, no);
+                    } else {
+                        const uint32_t u = b.read((int)(nl + nm + no));
+                        sl = (el >> 16) + (u >> (nm + no));
+                        sm = (em >> 16) + ((u >> no) & ((1u << nm) - 1));
+                        so = (eo >> 16) + (u & ((1u << no) - 1));
+                    }
                 }
                 // every decode-side failure of a sequence is the same status, so one test per sequence is enough
                 if (bad || b.pos < 0 || llen > lit_len - lp) { derr = CJ_ST_CORRUPT; cnt = k; break; }
