@@ -44,6 +44,14 @@ struct BitW {  // forward, LSB-first bit writer into global memory
         acc |= (uint64_t)(v & (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1))) << nb;
         nb += n;
     }
+    // v has no bits at or above n (n <= 32, nb + n <= 64): the caller packed several small fields into it with 32-bit operations, so
+    // the 64-bit shift is paid once per group instead of once per field
+    __device__ __forceinline__ void add_packed(uint32_t v, uint32_t n) {
+        const uint32_t s = nb & 31u;
+        const uint32_t lo = v << s, hi = s ? v >> (32u - s) : 0u;
+        acc |= nb < 32u ? ((uint64_t)hi << 32) | lo : (uint64_t)lo << 32;
+        nb += n;
+    }
     __device__ __forceinline__ void flush() {  // keeps < 8 bits pending; call at least every 56 added bits
         const uint32_t bytes = nb >> 3;
         if ((uint32_t)lane < bytes) p[pos + lane] = (uint8_t)(acc >> (8 * lane));
@@ -67,6 +75,13 @@ struct FseC {
     __device__ __forceinline__ void encode(BitW& w, const uint16_t* st, const int32_t* dnb, const int32_t* dfs, uint32_t sym) {
         const uint32_t nbo = (state + (uint32_t)dnb[sym]) >> 16;
         w.add(state, nbo);
+        state = st[(int32_t)(state >> nbo) + dfs[sym]];
+    }
+    // the same, but the state bits go behind the `n` bits already packed in `bits` instead of into the writer
+    __device__ __forceinline__ void encode_into(uint32_t& bits, uint32_t& n, const uint16_t* st, const int32_t* dnb, const int32_t* dfs, uint32_t sym) {
+        const uint32_t nbo = (state + (uint32_t)dnb[sym]) >> 16;   // <= 9
+        bits |= (state & ((1u << nbo) - 1u)) << n;
+        n += nbo;
         state = st[(int32_t)(state >> nbo) + dfs[sym]];
     }
 };
@@ -200,13 +215,19 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
     for (uint32_t k = nseq - 1; k-- > 0;) {
         const uint32_t ll = seq[3 * k], mlb = seq[3 * k + 1] - 3, ofv = seq[3 * k + 2] + 3;
         const uint32_t lc = ze_ll_code(ll), mc = ze_ml_code(mlb), oc = ze_hibit(ofv);
-        so.encode(w, g_ze.of_state, g_ze.of_dnb, g_ze.of_dfs, oc);   // <= 8 bits
-        sm.encode(w, g_ze.ml_state, g_ze.ml_dnb, g_ze.ml_dfs, mc);   // <= 9
-        sl.encode(w, g_ze.ll_state, g_ze.ll_dnb, g_ze.ll_dfs, lc);   // <= 9
-        w.flush();
-        w.add(ll, g_ze.ll_bits[lc]);                                  // <= 16
-        w.add(mlb, g_ze.ml_bits[mc]);                                 // <= 16
-        w.flush();
+        // the three state updates (<= 8 + 9 + 9 bits) are packed with 32-bit operations and added once; so are the two length
+        // fields (<= 16 + 16); then the offset (<= 17): at most 7 + 26 + 32 = 65 bits could be pending, so the writer is flushed
+        // after the states only when the lengths would not fit (rare) and once at the end of the sequence
+        uint32_t sb = 0, sn = 0;
+        so.encode_into(sb, sn, g_ze.of_state, g_ze.of_dnb, g_ze.of_dfs, oc);
+        sm.encode_into(sb, sn, g_ze.ml_state, g_ze.ml_dnb, g_ze.ml_dfs, mc);
+        sl.encode_into(sb, sn, g_ze.ll_state, g_ze.ll_dnb, g_ze.ll_dfs, lc);
+        w.add_packed(sb, sn);
+        const uint32_t lbits = g_ze.ll_bits[lc], mbits = g_ze.ml_bits[mc];
+        if (w.nb + lbits + mbits + oc > 64u) w.flush();               // afterwards < 8 pending: 7 + 32 + 17 <= 56
+        const uint32_t lm = (ll & ((1u << lbits) - 1u)) | ((lbits < 32u ? (mlb & ((1u << mbits) - 1u)) << lbits : 0u));
+        if (lbits + mbits <= 32u) w.add_packed(lm, lbits + mbits);
+        else { w.add(ll, lbits); w.add(mlb, mbits); }
         w.add(ofv, oc);                                               // <= 17
         w.flush();
         if (op + w.pos + 16 > bsz) return 0;  // not shrinking: store the block raw instead
