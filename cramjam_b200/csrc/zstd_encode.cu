@@ -212,8 +212,17 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
         w.add(ofv, oc);
         w.flush();
     }
-    for (uint32_t k = nseq - 1; k-- > 0;) {
-        const uint32_t ll = seq[3 * k], mlb = seq[3 * k + 1] - 3, ofv = seq[3 * k + 2] + 3;
+    // sequences are coded last to first; 32 of them are fetched at a time (lane j holds sequence top - j) and handed round by shuffle,
+    // so the serial loop does not wait for global memory
+    for (int64_t top = (int64_t)nseq - 2; top >= 0; top -= 32) {
+      const uint32_t cntb = top + 1 < 32 ? (uint32_t)(top + 1) : 32u;
+      uint32_t my_ll = 0, my_ml = 3, my_of = 0;
+      if ((uint32_t)lane < cntb) {
+          const uint32_t idx = (uint32_t)top - (uint32_t)lane;
+          my_ll = seq[3 * idx]; my_ml = seq[3 * idx + 1]; my_of = seq[3 * idx + 2];
+      }
+      for (uint32_t j = 0; j < cntb; j++) {
+        const uint32_t ll = __shfl_sync(FULL, my_ll, j), mlb = __shfl_sync(FULL, my_ml, j) - 3, ofv = __shfl_sync(FULL, my_of, j) + 3;
         const uint32_t lc = ze_ll_code(ll), mc = ze_ml_code(mlb), oc = ze_hibit(ofv);
         // the three state updates (<= 8 + 9 + 9 bits) are packed with 32-bit operations and added once; so are the two length
         // fields (<= 16 + 16); then the offset (<= 17): at most 7 + 26 + 32 = 65 bits could be pending, so the writer is flushed
@@ -231,6 +240,7 @@ __device__ uint32_t ze_block(const uint8_t* __restrict__ src, uint32_t b0, uint3
         w.add(ofv, oc);                                               // <= 17
         w.flush();
         if (op + w.pos + 16 > bsz) return 0;  // not shrinking: store the block raw instead
+      }
     }
     w.add(sm.state, 6);
     w.add(so.state, 5);
