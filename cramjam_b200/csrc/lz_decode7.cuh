@@ -281,7 +281,7 @@ G7_HD void decode_block(Env& env, bool has, const uint8_t* src, uint8_t* dst, ui
                 const bool isfar = !is_lit && !isnear && cn != 0;
                 const int32_t g0 = (int32_t)(sk & ~15u);   // far: output position of the first source granule (-16: in front of the block)
                 const uint32_t s0 = st_l + 2u * (uint32_t)u * GROW;   // ... and this slot's staging pair
-                env.cp16_far_if(s0, dst + (g0 < 0 ? 0 : g0), isfar && g0 >= 0);
+                env.cp16_far_if(s0, dst + (g0 < 0 ? 0 : g0), isfar && g0 >= 0 && dd + k < 16u);   // not if it would only hold the k bytes in front of the source
                 env.cp16_far_if(s0 + GROW, dst + (g0 + 16), isfar && dd + k + cn > 16u);   // second granule only if the chunk reaches into it
                 const uint32_t rbase = is_lit ? in_l : out_l;
                 const uint32_t rmask = is_lit ? (IN_G - 1) : (OUT_G - 1);
