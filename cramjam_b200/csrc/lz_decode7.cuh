@@ -5,7 +5,7 @@
 // (src/snappy.rs:52-60,102-108) and LZ4_decompress_safe behind lz4::block::decompress_into (src/lz4.rs:78-95,140-173).
 //
 // One THREAD per block, like generation 4 (lz_decode4.cu), rebuilt around what ncu showed of it and of this kernel's first
-// version (profiles/r02_g7_*): with 65 536 lanes at unrelated positions the kernel is bound by the SM's L1 / shared-memory
+// version (profiles/r02b_g7_*, profiles/README.md): with 65 536 lanes at unrelated positions the kernel is bound by the SM's L1 / shared-memory
 // data pipe — one wavefront per cycle, and a scattered 4-byte or 16-byte access of a warp costs a wavefront per bank conflict
 // or per cache line — long before it is bound by instruction issue.  So every access is made as wide and as conflict-free as
 // the format allows:
@@ -14,17 +14,19 @@
 //   * every per-lane structure in shared memory is a ring of 16-byte GRANULES, interleaved across the lanes of the warp
 //     (granule q of lane l at q * 512 + l * 16): a 16-byte access of a quarter warp then touches each bank once, whatever
 //     granule each lane is at.  The input ring has 8 granules (filled by 16-byte cp.async, two per pass), the ring of recent
-//     output 4, and every chunk in flight owns a staging pair;
+//     output 8, and every chunk in flight owns a staging pair;
 //   * a chunk's SOURCE is always two granules, read with two ld.shared.v4 into eight registers when the chunk retires: from the
-//     input ring (literal bytes), from the output ring (back-references of at most 32 bytes), or from the chunk's staging pair,
+//     input ring (literal bytes), from the output ring (back-references of at most 96 bytes), or from the chunk's staging pair,
 //     which one or two 16-byte cp.async filled from the block's own output in global memory one pass earlier (everything
 //     further back).  A two-stage select picks the six words the chunk starts in, five funnel shifts align them to the output
 //     phase.  (Fetching far sources with ld.global straight into the registers was measured and is slower: the loads of
 //     different slots share hardware scoreboards, so waiting for the oldest waits for the newest, profiles/README.md.)
 //   * the OUTPUT is assembled in registers: a second two-stage select places the five words at the output position inside a
-//     32-byte window whose lower half is the granule being filled; a finished granule is stored with one st.global.v4.  The
+//     32-byte window whose lower half is the granule being filled; a finished granule waits for its sector partner and the two
+//     leave with one 32-byte st.global.v8 (the kernel was bound by the number of L1 <-> L2 transactions, not by their size).  The
 //     partial granule is mirrored into the output ring every iteration, which is all a near back-reference needs;
-//   * a back-reference further than 32 bytes whose source is not yet in global memory waits for it (the chunk shrinks to what
+//   * selects on the retire path are integer multiply-adds (pick): the ALU pipe is the busy one, the FMA pipe idles;
+//   * a back-reference further than 96 bytes whose source is not yet in global memory waits for it (the chunk shrinks to what
 //     is there, or the lane issues nothing for an iteration); short periods double (1, 2, 4, 8, 16 bytes per chunk);
 //   * the last input granule is fetched with cp.async's src-size operand (the bytes beyond the block arrive as zeros), so the
 //     end of the input needs no separate path and nothing beyond the unit is read.
