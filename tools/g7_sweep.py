@@ -60,7 +60,18 @@ if REAL or NEAR or ORACLE:
     import oracle as O
     cdir = os.path.join(ROOT, "tests", "golden", "corpus")
     blobs = [] if not REAL else [np.frombuffer(bz2.decompress(open(os.path.join(cdir, f), "rb").read()), dtype=np.uint8) for f in sorted(os.listdir(cdir)) if f.endswith(".bz2")]
-    cdata = np.concatenate([b[: len(b) // U * U] for b in blobs]) if REAL else (near_blocks(128, NEAR) if NEAR else capi.synth_host(n, U))
+    CACHE = os.environ.get("SWEEP_CACHE")   # directory: host-made inputs are kept there between the processes of one A/B run
+    def cached(tag, make):
+        if not CACHE:
+            return make()
+        f = os.path.join(CACHE, f"g7sweep_{tag}_{n}.npy")
+        if os.path.exists(f):
+            return np.load(f)
+        a = make()
+        os.makedirs(CACHE, exist_ok=True)
+        np.save(f, a)
+        return a
+    cdata = np.concatenate([b[: len(b) // U * U] for b in blobs]) if REAL else (near_blocks(128, NEAR) if NEAR else cached("data", lambda: capi.synth_host(n, U)))
     nb = len(cdata) // U
     rep = max(1, n // nb)
     n = nb * rep
@@ -79,7 +90,14 @@ for name in codecs:
     if REAL or NEAR or ORACLE:
         comp = np.zeros(nb * slot + 64, dtype=np.uint8)
         so1, do1 = np.arange(nb, dtype=np.uint64) * np.uint64(U), np.arange(nb, dtype=np.uint64) * np.uint64(slot)
-        lens = O.batch(O.LZ4_BLOCK if name == "lz4" else O.SNAPPY_RAW, 1, cdata, so1, np.full(nb, U, np.uint64), comp, do1, np.full(nb, slot, np.uint64), nthreads=os.cpu_count())[0]
+        def encode():
+            lens = O.batch(O.LZ4_BLOCK if name == "lz4" else O.SNAPPY_RAW, 1, cdata, so1, np.full(nb, U, np.uint64), comp, do1, np.full(nb, slot, np.uint64), nthreads=os.cpu_count())[0]
+            return np.concatenate([lens.astype(np.uint64).view(np.uint8), comp])
+        if ORACLE and not REAL and not NEAR:
+            both = cached(f"comp_{name}", encode)
+        else:
+            both = encode()
+        lens, comp = both[:nb * 8].view(np.uint64).astype(np.int64), both[nb * 8:]
         assert (lens > 0).all()
         t_cmp = torch.from_numpy(comp).to(dev)
         t_co, t_cl = i64(np.tile(do1, rep)), i64(np.tile(lens.astype(np.uint64), rep))
