@@ -91,7 +91,7 @@ struct cj_ctx {
     unsigned* counters = nullptr;  // device work-queue counters
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
-    static constexpr int PIPE = 32;                // most chunks the pinned-arena pipeline may use (api.cu; CJ_PIPE_CHUNKS selects, default 16)
+    static constexpr int PIPE = 32;                // most chunks the pinned-arena pipeline may use (api.cu; CJ_PIPE_CHUNKS selects; default 32 from 1 GiB of payload, else 16; sizes ramp up, CJ_PIPE_RAMP=0 for equal chunks)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of that pipeline (created on first use)
     cudaEvent_t ev_in[PIPE] = {}, ev_k[PIPE] = {};
     uint64_t launches = 0;
