@@ -305,10 +305,10 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
     // measured at 65 536 x 64 KiB (tools/e2e_ab.py): 16 equal chunks 92.4 ms, 16 ramped 90.2-91.1, 32 ramped 89.4 (the link alone: 86.8)
     const int chunks = chunks_env ? chunks_env : (s_bytes + d_bytes >= ((size_t)1 << 30) ? 32 : 16);
     static const bool trace_ev = getenv("CJ_TRACE") != nullptr;
-    cudaEvent_t tr0 = nullptr, tr_in[cj_ctx::PIPE] = {}, tr_k0[cj_ctx::PIPE] = {}, tr_k1[cj_ctx::PIPE] = {};
+    cudaEvent_t tr0 = nullptr, tr_in[cj_ctx::PIPE] = {}, tr_k0[cj_ctx::PIPE] = {}, tr_k1[cj_ctx::PIPE] = {}, tr_out[cj_ctx::PIPE] = {};
     if (trace_ev) {
         cudaEventCreate(&tr0);
-        for (int i = 0; i < chunks; i++) { cudaEventCreate(&tr_in[i]); cudaEventCreate(&tr_k0[i]); cudaEventCreate(&tr_k1[i]); }
+        for (int i = 0; i < chunks; i++) { cudaEventCreate(&tr_in[i]); cudaEventCreate(&tr_k0[i]); cudaEventCreate(&tr_k1[i]); cudaEventCreate(&tr_out[i]); }
         cudaEventRecord(tr0, c->stream);
     }
     // Chunk sizes ramp up 1 : 2 : 4 : 8 : 16 : 16 ...: the output link is the bottleneck of a decode batch, and it idles until
@@ -355,16 +355,18 @@ static int run_pinned_pipelined(cj_ctx* c, int codec, bool compress, const cj_ba
         CUDA_TRY(cudaEventSynchronize(c->ev_k[k]));
         if (trace) fprintf(stderr, "[cj] chunk %d kernel done at %.2f ms\n", k, ms_now());
         if ((rc = copy_runs_home(c, bt, dl, a, b, d_lo, hd, c->s_d2h))) return rc;
+        if (trace_ev) cudaEventRecord(tr_out[k], c->s_d2h);
     }
     CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (trace) fprintf(stderr, "[cj] all output home at %.2f ms\n", ms_now());
     if (trace_ev) {
         for (int i = 0; i < chunks; i++) {
-            float a = 0, b = 0, d = 0;
+            float a = 0, b = 0, d = 0, o = 0;
             cudaEventElapsedTime(&a, tr0, tr_in[i]); cudaEventElapsedTime(&b, tr0, tr_k0[i]); cudaEventElapsedTime(&d, tr0, tr_k1[i]);
-            fprintf(stderr, "[cj] gpu timeline chunk %d: h2d done %.2f  kernel start %.2f  kernel end %.2f ms\n", i, a, b, d);
-            cudaEventDestroy(tr_in[i]); cudaEventDestroy(tr_k0[i]); cudaEventDestroy(tr_k1[i]);
+            cudaEventElapsedTime(&o, tr0, tr_out[i]);
+            fprintf(stderr, "[cj] gpu timeline chunk %d (units %zu..%zu): h2d done %.2f  kernel start %.2f  kernel end %.2f  d2h done %.2f ms\n", i, first[i], first[i + 1], a, b, d, o);
+            cudaEventDestroy(tr_in[i]); cudaEventDestroy(tr_k0[i]); cudaEventDestroy(tr_k1[i]); cudaEventDestroy(tr_out[i]);
         }
         cudaEventDestroy(tr0);
     }

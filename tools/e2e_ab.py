@@ -55,6 +55,26 @@ for _ in range(6):
     t0 = time.perf_counter()
     step()
     times.append(1e3 * (time.perf_counter() - t0))
-print(f"e2e CJ_PIPE_CHUNKS={os.environ.get('CJ_PIPE_CHUNKS', '16')} CJ_PIPE_RAMP={os.environ.get('CJ_PIPE_RAMP', '1')}: "
+if os.environ.get("E2E_LINK"):   # what plain copies of the same bytes do on this box: both directions at once, and each alone
+    d_c = torch.empty(span + 64, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    def timed(f):
+        torch.cuda.synchronize(); f(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); f(); torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0)
+    def both():
+        with torch.cuda.stream(s1): d_c.copy_(h_comp, non_blocking=True)
+        with torch.cuda.stream(s2): h_out.copy_(raw, non_blocking=True)
+    def h2d():
+        with torch.cuda.stream(s1): d_c.copy_(h_comp, non_blocking=True)
+    def d2h():
+        with torch.cuda.stream(s2): h_out.copy_(raw, non_blocking=True)
+    def both_chunked(k=32):
+        cs, co = (span + k - 1) // k, (n * U + k - 1) // k
+        for i in range(k):
+            with torch.cuda.stream(s1): d_c[i * cs:(i + 1) * cs].copy_(h_comp[i * cs:(i + 1) * cs], non_blocking=True)
+            with torch.cuda.stream(s2): h_out[i * co:(i + 1) * co].copy_(raw[i * co:(i + 1) * co], non_blocking=True)
+    print(f"link: both {timed(both):.2f} ms  both in 32 pieces {timed(both_chunked):.2f} ms  h2d alone {timed(h2d):.2f} ms ({span / 1e9:.2f} GB)  d2h alone {timed(d2h):.2f} ms ({n * U / 1e9:.2f} GB)", flush=True)
+print(f"e2e CJ_PIPE_CHUNKS={os.environ.get('CJ_PIPE_CHUNKS', 'default')} CJ_PIPE_RAMP={os.environ.get('CJ_PIPE_RAMP', '1')}: "
       f"median {np.median(times):.2f} ms  best {min(times):.2f} ms  -> {n * U / np.median(times) / 1e6:.2f} GB/s uncompressed  "
       f"(h2d {span / 1e9:.2f} GB, d2h {n * U / 1e9:.2f} GB)", flush=True)
