@@ -139,3 +139,36 @@ def test_hostile_streams(codec):
             n += 1
             acc += r >= 0
     assert acc > n // 20   # mutations that leave the stream valid are still decoded by the lane itself
+
+
+@pytest.mark.parametrize("codec", [SNAPPY, LZ4])
+def test_real_corpus_blocks(codec):
+    """64 KiB blocks of the six Silesia files the reference's benchmarks ship (tests/golden/corpus), encoded by the oracle and, where
+    they are installed, by Google snappy / liblz4 (fast and HC): text, XML, a chemical database with very long matches, an
+    executable, a medical image — element mixes the synthetic generator does not produce."""
+    import bz2
+    import syslibs as S
+    U = 65536
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus")
+    encoders = [COMP[codec]]
+    if codec == SNAPPY:
+        try:
+            S.snappy_compress(b"probe")
+            encoders.append(S.snappy_compress)   # Google snappy (pyarrow's copy)
+        except Exception:
+            pass
+    if codec == LZ4 and S.have_lz4:
+        encoders += [lambda d: S.lz4_compress(d, accel=1), lambda d: S.lz4_compress(d, hc=9)]
+    n = 0
+    for f in sorted(os.listdir(cdir)):
+        if not f.endswith(".bz2"):
+            continue
+        raw = bz2.decompress(open(os.path.join(cdir, f), "rb").read())
+        nb = len(raw) // U
+        for b in (0, nb // 2, nb - 1):
+            blk = raw[b * U:(b + 1) * U]
+            for e, enc in enumerate(encoders):
+                r, _ = check(codec, enc(blk), U, depth=3, mode=(b + e) & 1)
+                assert r == U, (f, b, e)
+                n += 1
+    assert n >= 18
