@@ -74,6 +74,31 @@ if os.environ.get("E2E_LINK"):   # what plain copies of the same bytes do on thi
         for i in range(k):
             with torch.cuda.stream(s1): d_c[i * cs:(i + 1) * cs].copy_(h_comp[i * cs:(i + 1) * cs], non_blocking=True)
             with torch.cuda.stream(s2): h_out[i * co:(i + 1) * co].copy_(raw[i * co:(i + 1) * co], non_blocking=True)
+    def both_paced(k=32, lead=2):
+        # input pieces issued just in time: piece i + lead goes out when output piece i is done (the input link idles in between)
+        cs, co = (span + k - 1) // k, (n * U + k - 1) // k
+        evs = []
+        for i in range(min(lead, k)):
+            with torch.cuda.stream(s1): d_c[i * cs:(i + 1) * cs].copy_(h_comp[i * cs:(i + 1) * cs], non_blocking=True)
+        for i in range(k):
+            with torch.cuda.stream(s2):
+                h_out[i * co:(i + 1) * co].copy_(raw[i * co:(i + 1) * co], non_blocking=True)
+                e = torch.cuda.Event(); e.record(s2); evs.append(e)
+            j = i + lead
+            if j < k:
+                if i >= 1: evs[i - 1].synchronize()
+                with torch.cuda.stream(s1): d_c[j * cs:(j + 1) * cs].copy_(h_comp[j * cs:(j + 1) * cs], non_blocking=True)
+    def pieces(kh, kd):
+        def f():
+            cs, co = (span + kh - 1) // kh if kh else 0, (n * U + kd - 1) // kd if kd else 0
+            for i in range(max(kh, kd)):
+                if i < kh:
+                    with torch.cuda.stream(s1): d_c[i * cs:(i + 1) * cs].copy_(h_comp[i * cs:(i + 1) * cs], non_blocking=True)
+                if i < kd:
+                    with torch.cuda.stream(s2): h_out[i * co:(i + 1) * co].copy_(raw[i * co:(i + 1) * co], non_blocking=True)
+        return f
+    print("link pieces (input x output -> ms): " + "  ".join(f"{a}x{b} {timed(pieces(a, b)):.2f}" for a, b in ((0, 1), (0, 32), (1, 0), (32, 0), (1, 32), (32, 1), (8, 8), (16, 16), (32, 32))), flush=True)
+    print(f"link paced: lead 2 {timed(both_paced):.2f} ms  lead 4 {timed(lambda: both_paced(32, 4)):.2f} ms  lead 8 {timed(lambda: both_paced(32, 8)):.2f} ms", flush=True)
     print(f"link: both {timed(both):.2f} ms  both in 32 pieces {timed(both_chunked):.2f} ms  h2d alone {timed(h2d):.2f} ms ({span / 1e9:.2f} GB)  d2h alone {timed(d2h):.2f} ms ({n * U / 1e9:.2f} GB)", flush=True)
 print(f"e2e CJ_PIPE_CHUNKS={os.environ.get('CJ_PIPE_CHUNKS', 'default')} CJ_PIPE_RAMP={os.environ.get('CJ_PIPE_RAMP', '1')}: "
       f"median {np.median(times):.2f} ms  best {min(times):.2f} ms  -> {n * U / np.median(times) / 1e6:.2f} GB/s uncompressed  "
